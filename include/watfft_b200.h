@@ -1,0 +1,140 @@
+/*
+ * watfft_b200.h -- C ABI of the B200-native batched FFT engine.
+ *
+ * This is the drop-in boundary for wat-fft's transform path: the entry points
+ * below are what the N-API addon (wat-fft_b200/napi/watfft_napi.cc), the JS
+ * loader (wat-fft_b200/js/index.js) and the pytest/ctypes harness bind.  Plain
+ * pointers and sizes only; no C++/torch types cross it; no exceptions or
+ * longjmp cross it (int error codes + wfb_strerror).
+ *
+ * What each call replaces in the reference (file:line under EmNudge/wat-fft):
+ *
+ *   wfb_plan_create   <- loadWasm()+instantiate (index.js:13-18) followed by the module's
+ *                        precompute export: precompute_twiddles_split / precompute_rfft_twiddles_split
+ *                        (modules/fft_split_native_f32.wat:151, :1167), precompute_twiddles
+ *                        (modules/fft_stockham_f32_dual.wat:117, modules/fft_combined.wat:111),
+ *                        precompute_rfft_twiddles (modules/fft_real_combined.wat:931).
+ *   wfb_host_in/out   <- `new Float32Array(exports.memory.buffer, off, len)` views
+ *                        (index.js:78-83, :107-112, :136-141, :165-170; REAL_OFFSET/IMAG_OFFSET
+ *                        of modules/fft_split_native_f32.wat:60-61).
+ *   wfb_exec(FORWARD) <- exports.fft_split / rfft_split (fft_split_native_f32.wat:2001, :1578),
+ *                        exports.fft (fft_stockham_f32_dual.wat:1314, fft_combined.wat:727),
+ *                        exports.rfft (fft_real_combined.wat:953).
+ *   wfb_exec(INVERSE) <- exports.ifft_split / irfft_split (fft_split_native_f32.wat:2124, :1945),
+ *                        exports.ifft (fft_stockham_f32_dual.wat:1329, fft_combined.wat:823).
+ *                        f64 c2r has no reference implementation (index.js:145-147 calls a
+ *                        missing export); it is provided as an extension.
+ *   wfb_plan_destroy  <- garbage collection of the WebAssembly.Instance (new obligation).
+ *
+ * Batched buffer layout (reduces to the reference's memory map at batch = 1):
+ *   C2C SPLIT        plane 0 = re[batch][n], plane 1 = im[batch][n]            (in place)
+ *   C2C INTERLEAVED  plane 0 = [batch][2n]  (re,im pairs)                      (in place)
+ *   R2C              time plane  = [batch][n] reals,
+ *                    spectrum    = [batch][n+2]  (n/2+1 interleaved bins)
+ *                    FORWARD reads time, writes spectrum; INVERSE the opposite.
+ *                    At batch = 1 the two host views alias (same bytes, like index.js:136-141).
+ * All transforms are unnormalised forward / 1/n-normalised inverse, natural bin order.
+ *
+ * Threading: a plan is not re-entrant; distinct plans are independent and may be driven from
+ * distinct host threads.  Each plan binds one device and one stream.
+ * There is NO CPU fallback: every entry point fails with WFB_ERR_NO_DEVICE when no sm_100
+ * device is present.
+ */
+#ifndef WATFFT_B200_H
+#define WATFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define WFB_API __declspec(dllexport)
+#else
+#define WFB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct wfb_plan wfb_plan;
+
+enum { WFB_C2C = 0, WFB_R2C = 1 };                 /* kind */
+enum { WFB_F32 = 0, WFB_F64 = 1 };                 /* precision */
+enum { WFB_SPLIT = 0, WFB_INTERLEAVED = 1 };       /* layout (C2C only) */
+enum { WFB_FORWARD = 0, WFB_INVERSE = 1 };         /* direction */
+enum { WFB_STAGE_H2D = 1, WFB_STAGE_D2H = 2, WFB_SYNC = 4, WFB_EXEC_DEFAULT = 7 };   /* exec flags */
+enum { WFB_BUF_TIME = 0, WFB_BUF_SPECTRUM = 1 };   /* R2C buffer ids for wfb_*_buffer */
+
+enum {
+    WFB_OK = 0,
+    WFB_ERR_NO_DEVICE = -1,     /* no CUDA device, or device is not sm_100 (B200) */
+    WFB_ERR_BAD_SIZE = -2,      /* n not a power of two or outside the supported range */
+    WFB_ERR_BAD_ARG = -3,
+    WFB_ERR_UNSUPPORTED = -4,   /* (kind, precision, layout) combination not provided */
+    WFB_ERR_ALLOC = -5,
+    WFB_ERR_CUDA = -6,          /* see wfb_last_cuda_error() */
+    WFB_ERR_NO_HOST_BUFFERS = -7
+};
+
+/* ---- device discovery ------------------------------------------------ */
+WFB_API int wfb_device_count(void);
+/* 0 when `device` is an sm_100 part; WFB_ERR_NO_DEVICE otherwise (the JS factory throws on it). */
+WFB_API int wfb_require_b200(int device);
+WFB_API const char *wfb_strerror(int code);
+WFB_API const char *wfb_last_cuda_error(void);
+
+/* ---- supported sizes -------------------------------------------------- */
+/* Writes the inclusive [min_n, max_n] range for a combination; returns WFB_OK or WFB_ERR_UNSUPPORTED.
+ * Works without a GPU (pure host logic). */
+WFB_API int wfb_size_range(int kind, int precision, int layout, int *min_n, int *max_n);
+
+/* ---- plans ------------------------------------------------------------- */
+/* flags for wfb_plan_create_ex */
+enum { WFB_PLAN_NO_HOST_BUFFERS = 1,    /* device-resident use only (bench / multi-GPU driver) */
+       WFB_PLAN_NO_DEVICE_BUFFERS = 2   /* caller supplies device pointers to wfb_exec_device */ };
+
+WFB_API wfb_plan *wfb_plan_create(int kind, int precision, int layout, int n, long batch, int device, int *err);
+WFB_API wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long batch, int device,
+                                     int flags, int *err);
+WFB_API void wfb_plan_destroy(wfb_plan *plan);
+
+/* Pinned host staging buffers, stable for the lifetime of the plan.
+ *   C2C: plane 0 (re or interleaved), plane 1 (im; NULL for INTERLEAVED); in == out.
+ *   R2C: wfb_host_in(plan, dir-agnostic plane) -- use wfb_host_buffer(plan, WFB_BUF_TIME|WFB_BUF_SPECTRUM). */
+WFB_API void *wfb_host_in(wfb_plan *plan, int plane);
+WFB_API void *wfb_host_out(wfb_plan *plan, int plane);
+WFB_API void *wfb_host_buffer(wfb_plan *plan, int which);
+WFB_API size_t wfb_host_bytes(wfb_plan *plan, int which);
+WFB_API void *wfb_device_buffer(wfb_plan *plan, int which);
+
+/* Runs `direction` over the plan's own buffers.  flags = WFB_EXEC_DEFAULT reproduces the reference's
+ * synchronous forward()/inverse(): H2D of the input view, kernel, D2H of the output view, sync. */
+WFB_API int wfb_exec(wfb_plan *plan, int direction, int flags);
+
+/* Device-pointer entry (bench harness, multi-GPU driver).  d_in/d_out hold two plane pointers
+ * (second unused unless C2C SPLIT).  `stream` is a cudaStream_t (NULL = the plan's stream).
+ * In-place (d_in == d_out) is allowed for C2C and for R2C at batch = 1. */
+WFB_API int wfb_exec_device(wfb_plan *plan, int direction, const void *const d_in[2], void *const d_out[2],
+                            void *stream);
+WFB_API int wfb_sync(wfb_plan *plan);
+WFB_API void *wfb_plan_stream(wfb_plan *plan);
+
+/* ---- introspection / tuning ------------------------------------------- */
+/* Kernel variants compiled for this plan's (kind, precision, n); variant 0 is the default. */
+WFB_API int wfb_plan_variant_count(wfb_plan *plan);
+WFB_API int wfb_plan_set_variant(wfb_plan *plan, int variant);
+WFB_API const char *wfb_plan_variant_name(wfb_plan *plan, int variant);
+/* Algorithmic bytes one exec moves (one read + one write of the payload; twiddles excluded). */
+WFB_API size_t wfb_plan_algorithmic_bytes(wfb_plan *plan);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+WFB_API unsigned long long wfb_kernel_launch_count(void);
+
+/* Host-side reference-exact twiddle generation (no GPU needed): fills re/im[count] with the
+ * W_n^k table the reference's precompute export would build.  flavour: 0 = f32 split module,
+ * 1 = f32 interleaved module, 2 = f64 modules.  re/im are float* for 0/1, double* for 2. */
+WFB_API int wfb_reference_twiddles(int flavour, int n, int count, void *re, void *im);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WATFFT_B200_H */

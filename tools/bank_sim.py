@@ -1,0 +1,121 @@
+#!/usr/bin/env python3
+"""Shared-memory bank-conflict simulator for the exchange patterns of wfb_kernels.cuh.
+
+For a plan (N, T, pass codes) and a pad rule (one pad slot per PADQ complex elements) it replays
+every warp-wide smem write (tid + e*T) and read (Rp*s'*j + t' + k*s') of every exchange and reports
+the worst wavefront multiplicity per instruction.  Model: 32 banks x 4 B; an access of W bytes per
+thread is served in phases of 128/W threads (16 for float2, 8 for double2); within a phase the cost
+is the max number of distinct 4-byte words that fall in one bank.
+"""
+import sys
+from itertools import product
+
+
+def nsub(code):
+    n = 0
+    while code:
+        n += 1
+        code >>= 4
+    return n
+
+
+def radix(code, q):
+    return (code >> (4 * (nsub(code) - 1 - q))) & 0xF
+
+
+def rp(code):
+    r = 1
+    while code:
+        r *= code & 0xF
+        code >>= 4
+    return r
+
+
+def slot_to_out(code, k):
+    g, w, mult, out = nsub(code), rp(code), 1, 0
+    for a in range(g):
+        r = radix(code, a)
+        w //= r
+        d = (k // w) % r
+        out += d * mult
+        mult *= r
+    return out
+
+
+def conflicts(addrs_words, width_words):
+    """addrs_words: list of 32 starting word addresses (one per lane); returns wavefronts needed."""
+    per_phase = 32 // width_words if width_words > 1 else 32
+    per_phase = {1: 32, 2: 16, 4: 8}[width_words]
+    total = 0
+    for ph in range(0, 32, per_phase):
+        banks = {}
+        for a in addrs_words[ph:ph + per_phase]:
+            if a is None:
+                continue
+            for w in range(width_words):
+                banks.setdefault((a + w) % 32, set()).add(a + w)
+        total += max((len(v) for v in banks.values()), default=0)
+    return total, 32 // per_phase
+
+
+def simulate(N, T, codes, padq, elem_words, X=None, verbose=False):
+    E = N // T
+    X = X or max(1, 256 // T)
+    S = N + (N // padq if padq else 0)
+    pad = (lambda p: p + p // padq) if padq else (lambda p: p)
+    worst_w, worst_r = 1.0, 1.0
+    nthreads = T * X
+    lin = 1
+    for P in range(len(codes) - 1):
+        code = codes[P]
+        RP = rp(code)
+        NB = E // RP
+        lin *= RP
+        # writes
+        for i, k in product(range(NB), range(RP)):
+            e = i + NB * slot_to_out(code, k)
+            for w0 in range(0, nthreads, 32):
+                addrs = []
+                for lane in range(32):
+                    th = w0 + lane
+                    xi, tid = th // T, th % T
+                    addrs.append((xi * S + pad(tid + e * T)) * elem_words)
+                c, ideal = conflicts(addrs, elem_words)
+                worst_w = max(worst_w, c / ideal)
+        code2 = codes[P + 1]
+        RP2 = rp(code2)
+        NB2 = E // RP2
+        SP2 = N // (lin * RP2)
+        for i, k in product(range(NB2), range(RP2)):
+            for w0 in range(0, nthreads, 32):
+                addrs = []
+                for lane in range(32):
+                    th = w0 + lane
+                    xi, tid = th // T, th % T
+                    b = tid + i * T
+                    j, t = b // SP2, b % SP2
+                    addrs.append((xi * S + pad(RP2 * SP2 * j + t + k * SP2)) * elem_words)
+                c, ideal = conflicts(addrs, elem_words)
+                worst_r = max(worst_r, c / ideal)
+    return worst_w, worst_r
+
+
+PLANS_F32 = {
+    32: (2, [0x2, 0x44]), 64: (4, [0x4, 0x44]), 128: (8, [0x24, 0x44]), 256: (16, [0x44, 0x44]),
+    512: (32, [0x2, 0x44, 0x44]), 1024: (64, [0x4, 0x44, 0x44]), 2048: (128, [0x24, 0x44, 0x44]),
+    4096: (256, [0x44, 0x44, 0x44]), 8192: (512, [0x2, 0x44, 0x44, 0x44]),
+}
+PLANS_F64 = {
+    32: (2, [0x2, 0x2222]), 64: (4, [0x4, 0x44]), 128: (8, [0x222, 0x2222]), 256: (16, [0x44, 0x44]),
+    512: (32, [0x2, 0x2222, 0x2222]), 1024: (64, [0x4, 0x44, 0x44]), 2048: (128, [0x222, 0x2222, 0x2222]),
+    4096: (256, [0x44, 0x44, 0x44]), 8192: (512, [0x2, 0x2222, 0x2222, 0x2222]),
+}
+
+if __name__ == "__main__":
+    for name, plans, ew in (("f32", PLANS_F32, 2), ("f64", PLANS_F64, 4)):
+        for padq in (0, 4, 8, 16, 32):
+            row = []
+            for n, (t, codes) in plans.items():
+                w, r = simulate(n, t, codes, padq, ew)
+                row.append(f"{n}:{w:.0f}/{r:.0f}")
+            print(name, "padq", padq, " ".join(row))

@@ -1,0 +1,458 @@
+// wfb_api.cu -- C ABI (include/watfft_b200.h) over the sm_100a kernels of wfb_kernels.cuh.
+//
+// Plans own: reference-exact twiddle tables (host-built, uploaded once), device buffers laid out
+// [batch][row], optional pinned host staging buffers that the JS side wraps as ArrayBuffers, and a
+// stream.  There is no CPU path anywhere in this file: without an sm_100 device every call fails.
+#include "../../include/watfft_b200.h"
+#include "wfb_kernels.cuh"
+#include "wfb_twiddle.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
+#include <string>
+#include <vector>
+
+namespace wfb {
+
+static thread_local char g_cuda_err[256] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return WFB_ERR_CUDA;
+}
+#define CK(call)                                                 \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);      \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------
+// variant registry
+// ----------------------------------------------------------------------------------------
+typedef cudaError_t (*launch_fn)(int io, int dir, const KParams &p, long batch, cudaStream_t s);
+
+struct Variant {
+    const char *name;
+    int core_n;        // complex points of the core transform (n for C2C, n/2 for R2C)
+    int threads;       // per CTA
+    int rows_per_cta;  // X
+    size_t smem;       // dynamic shared memory per CTA
+    std::vector<int> radices;
+    launch_fn c2c, r2c, c2r;
+};
+
+template <class PL> static std::vector<int> plan_radices() {
+    std::vector<int> r;
+    for (int p = 0; p < PL::npass(); p++)
+        for (int q = 0; q < pass_nsub(PL::code(p)); q++) r.push_back(pass_radix(PL::code(p), q));
+    return r;
+}
+
+template <typename K> static cudaError_t launch_kernel(K kernel, size_t smem, int threads, long batch, int X,
+                                                       const KParams &p, cudaStream_t s) {
+    // the dynamic-smem attribute is per (device, function); set it once for each pair
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> configured;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto key = std::make_pair(dev, (const void *)kernel);
+        if (!configured.count(key)) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured.insert(key);
+        }
+    }
+    long grid = (batch + X - 1) / X;
+    kernel<<<dim3((unsigned)grid), dim3(threads), smem, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+constexpr int PADQ = 16;   // one pad slot per 16 complex values: conflict-free for every plan (tools/bank_sim.py)
+
+template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers {
+    static constexpr size_t smem = sizeof(vec2<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
+    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
+        if constexpr (SPLIT_IO) {
+            if (io == IO_SPLIT) {
+                if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, true, MINB>, smem, PL::T * X, batch, X, p, s);
+                return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, false, MINB>, smem, PL::T * X, batch, X, p, s);
+            }
+        }
+        if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB>, smem, PL::T * X, batch, X, p, s);
+        return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB>, smem, PL::T * X, batch, X, p, s);
+    }
+    static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_kernel(k_r2c<R, PL, X, PADQ, MINB>, smem, PL::T * X, batch, X, p, s);
+    }
+    static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_kernel(k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, batch, X, p, s);
+    }
+    static Variant make(const char *name) {
+        return Variant{name, PL::N, PL::T * X, X, smem, plan_radices<PL>(), &c2c, &r2c, &c2r};
+    }
+};
+
+#define XROWS(T) ((T) >= 256 ? 1 : 256 / (T))
+
+// f32 core plans: the reference's split-core stage structure (radix-4, leading radix-2 for odd log2)
+using F32_4 = Plan<4, 1, 0x4>;
+using F32_8 = Plan<8, 1, 0x222>;
+using F32_16 = Plan<16, 1, 0x44>;
+using F32_32 = Plan<32, 2, 0x2, 0x44>;
+using F32_64 = Plan<64, 4, 0x4, 0x44>;
+using F32_128 = Plan<128, 8, 0x24, 0x44>;
+using F32_256 = Plan<256, 16, 0x44, 0x44>;
+using F32_512 = Plan<512, 32, 0x2, 0x44, 0x44>;
+using F32_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
+using F32_2048 = Plan<2048, 128, 0x24, 0x44, 0x44>;
+using F32_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
+using F32_8192 = Plan<8192, 512, 0x2, 0x44, 0x44, 0x44>;
+// f64 core plans: radix-4 for N = 4^p, radix-2 otherwise (fft_combined.wat:727-732)
+using F64_4 = Plan<4, 1, 0x4>;
+using F64_8 = Plan<8, 1, 0x222>;
+using F64_16 = Plan<16, 1, 0x44>;
+using F64_32 = Plan<32, 2, 0x2, 0x2222>;
+using F64_64 = Plan<64, 4, 0x4, 0x44>;
+using F64_128 = Plan<128, 8, 0x222, 0x2222>;
+using F64_256 = Plan<256, 16, 0x44, 0x44>;
+using F64_512 = Plan<512, 32, 0x2, 0x2222, 0x2222>;
+using F64_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
+using F64_2048 = Plan<2048, 128, 0x222, 0x2222, 0x2222>;
+using F64_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
+using F64_8192 = Plan<8192, 512, 0x2, 0x2222, 0x2222, 0x2222>;
+
+#define V32(PL, MINB) Launchers<float, PL, XROWS(PL::T), MINB, true>::make(#PL)
+#define V64(PL, MINB) Launchers<double, PL, XROWS(PL::T), MINB, false>::make(#PL)
+
+static const std::vector<Variant> &variants_f32() {
+    static const std::vector<Variant> v = {
+        V32(F32_4, 2), V32(F32_8, 2), V32(F32_16, 2), V32(F32_32, 2), V32(F32_64, 2), V32(F32_128, 2),
+        V32(F32_256, 2), V32(F32_512, 2), V32(F32_1024, 2), V32(F32_2048, 2), V32(F32_4096, 2), V32(F32_8192, 1),
+    };
+    return v;
+}
+static const std::vector<Variant> &variants_f64() {
+    static const std::vector<Variant> v = {
+        V64(F64_4, 2), V64(F64_8, 2), V64(F64_16, 2), V64(F64_32, 2), V64(F64_64, 2), V64(F64_128, 2),
+        V64(F64_256, 2), V64(F64_512, 2), V64(F64_1024, 2), V64(F64_2048, 2), V64(F64_4096, 1), V64(F64_8192, 1),
+    };
+    return v;
+}
+
+static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
+static int ilog2(long n) { int k = 0; while ((1L << k) < n) k++; return k; }
+
+}  // namespace wfb
+
+using namespace wfb;
+
+// ----------------------------------------------------------------------------------------
+// plan object
+// ----------------------------------------------------------------------------------------
+struct wfb_plan {
+    int kind, precision, layout, n, device, flags;
+    long batch;
+    int core_n;
+    size_t elem;                       // sizeof(real)
+    std::vector<const Variant *> variants;
+    int variant;
+    void *d_tw_fwd[8], *d_tw_inv[8];   // per variant
+    void *d_rtw;
+    // buffers: C2C -> plane 0 / plane 1; R2C -> time / spectrum
+    void *d_buf[2];
+    void *h_buf[2];
+    size_t bytes[2];
+    bool host_alias;                   // R2C batch == 1: both host views share one allocation
+    cudaStream_t stream;
+};
+
+static int check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        snprintf(g_cuda_err, sizeof g_cuda_err, "no usable CUDA device (%s)", e == cudaSuccess ? "index out of range" : cudaGetErrorString(e));
+        return WFB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WFB_ERR_NO_DEVICE;
+    if (prop.major != 10) {   // kernels are built for sm_100a only
+        snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d, need sm_100 (B200)", device, prop.major, prop.minor);
+        return WFB_ERR_NO_DEVICE;
+    }
+    return WFB_OK;
+}
+
+extern "C" {
+
+int wfb_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+int wfb_require_b200(int device) { return check_device(device); }
+
+const char *wfb_strerror(int code) {
+    switch (code) {
+        case WFB_OK: return "ok";
+        case WFB_ERR_NO_DEVICE: return "no B200 (sm_100) device available; this engine has no CPU fallback";
+        case WFB_ERR_BAD_SIZE: return "transform size must be a power of two within the supported range";
+        case WFB_ERR_BAD_ARG: return "bad argument";
+        case WFB_ERR_UNSUPPORTED: return "unsupported (kind, precision, layout) combination";
+        case WFB_ERR_ALLOC: return "allocation failed";
+        case WFB_ERR_CUDA: return "CUDA error (see wfb_last_cuda_error)";
+        case WFB_ERR_NO_HOST_BUFFERS: return "plan was created without host staging buffers";
+        default: return "unknown error";
+    }
+}
+
+const char *wfb_last_cuda_error(void) { return g_cuda_err; }
+
+int wfb_size_range(int kind, int precision, int layout, int *min_n, int *max_n) {
+    int lo, hi;
+    if (kind == WFB_C2C) {
+        if (precision == WFB_F32 && (layout == WFB_SPLIT || layout == WFB_INTERLEAVED)) { lo = 4; hi = 8192; }
+        else if (precision == WFB_F64 && layout == WFB_INTERLEAVED) { lo = 4; hi = 8192; }
+        else return WFB_ERR_UNSUPPORTED;
+    } else if (kind == WFB_R2C) {
+        if (precision == WFB_F32) { lo = 32; hi = 16384; }     // rfft_split requires n >= 32 (fft_split_native_f32.wat:1562)
+        else if (precision == WFB_F64) { lo = 8; hi = 16384; }
+        else return WFB_ERR_UNSUPPORTED;
+    } else return WFB_ERR_UNSUPPORTED;
+    if (min_n) *min_n = lo;
+    if (max_n) *max_n = hi;
+    return WFB_OK;
+}
+
+int wfb_reference_twiddles(int flavour, int n, int count, void *re, void *im) {
+    if (!re || !im || n <= 0 || count < 0) return WFB_ERR_BAD_ARG;
+    if (flavour == TW_F64) {
+        std::vector<double> r, i;
+        base_twiddles<double>(TW_F64, n, count, r, i);
+        memcpy(re, r.data(), sizeof(double) * count); memcpy(im, i.data(), sizeof(double) * count);
+    } else if (flavour == TW_F32_SPLIT || flavour == TW_F32_DUAL) {
+        std::vector<float> r, i;
+        base_twiddles<float>(flavour, n, count, r, i);
+        memcpy(re, r.data(), sizeof(float) * count); memcpy(im, i.data(), sizeof(float) * count);
+    } else return WFB_ERR_BAD_ARG;
+    return WFB_OK;
+}
+
+}  // extern "C"
+
+// builds forward / inverse stage tables for one variant and uploads them
+template <typename R>
+static int upload_tables(wfb_plan *pl, int vi) {
+    const Variant &v = *pl->variants[vi];
+    const int m = v.core_n;
+    int flavour;
+    if (sizeof(R) == 8) flavour = (m == 16 || m <= 4) ? TW_EXACT : TW_F64;
+    else if (pl->kind == WFB_C2C && pl->layout == WFB_INTERLEAVED) flavour = (m <= 16) ? TW_EXACT : TW_F32_DUAL;
+    else flavour = TW_F32_SPLIT;
+    std::vector<R> bre, bim, fwd, inv;
+    base_twiddles<R>(flavour, m, m, bre, bim);
+    stage_tables<R>(v.radices, m, bre, bim, false, fwd);
+    stage_tables<R>(v.radices, m, bre, bim, true, inv);
+    if (pl->kind == WFB_R2C && sizeof(R) == 4 && (ilog2(m) & 1) && m >= 32 && v.radices.size() >= 2 &&
+        v.radices[0] == 2 && v.radices[1] == 4) {
+        // rfft_split's fused radix-8 opening uses exact W_8 constants for group 1 of the l = 2 stage
+        // (fft_split_native_f32.wat:1199-1371); forward table only.
+        const R c = R(0.7071067811865476);
+        size_t off = 2 * 1;                 // skip the radix-2 stage's single entry (re,im)
+        const int l = 2;
+        R w[3][2] = {{c, -c}, {R(0), R(-1)}, {-c, -c}};
+        for (int mm = 0; mm < 3; mm++) { fwd[off + 2 * (mm * l + 1)] = w[mm][0]; fwd[off + 2 * (mm * l + 1) + 1] = w[mm][1]; }
+    }
+    if (fwd.empty()) { fwd.assign(2, R(0)); inv.assign(2, R(0)); }
+    CK(cudaMalloc(&pl->d_tw_fwd[vi], fwd.size() * sizeof(R)));
+    CK(cudaMalloc(&pl->d_tw_inv[vi], inv.size() * sizeof(R)));
+    CK(cudaMemcpy(pl->d_tw_fwd[vi], fwd.data(), fwd.size() * sizeof(R), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pl->d_tw_inv[vi], inv.data(), inv.size() * sizeof(R), cudaMemcpyHostToDevice));
+    if (pl->kind == WFB_R2C && vi == 0) {
+        // W_n^k, k = 0..M (fft_split_native_f32.wat:1167-1191; fft_real_combined.wat:931-948)
+        int rf = sizeof(R) == 8 ? ((pl->n == 8 || pl->n == 32) ? TW_EXACT : TW_F64) : TW_F32_SPLIT;
+        std::vector<R> rre, rim, packed;
+        base_twiddles<R>(rf, pl->n, m + 1, rre, rim);
+        for (int k = 0; k <= m; k++) { packed.push_back(rre[k]); packed.push_back(rim[k]); }
+        CK(cudaMalloc(&pl->d_rtw, packed.size() * sizeof(R)));
+        CK(cudaMemcpy(pl->d_rtw, packed.data(), packed.size() * sizeof(R), cudaMemcpyHostToDevice));
+    }
+    return WFB_OK;
+}
+
+static int plan_init(wfb_plan *pl) {
+    CK(cudaSetDevice(pl->device));
+    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    for (size_t vi = 0; vi < pl->variants.size(); vi++) {
+        int rc = pl->precision == WFB_F64 ? upload_tables<double>(pl, (int)vi) : upload_tables<float>(pl, (int)vi);
+        if (rc) return rc;
+    }
+    const size_t e = pl->elem, n = (size_t)pl->n, b = (size_t)pl->batch;
+    if (pl->kind == WFB_C2C) {
+        if (pl->layout == WFB_SPLIT) { pl->bytes[0] = pl->bytes[1] = e * n * b; }
+        else { pl->bytes[0] = 2 * e * n * b; pl->bytes[1] = 0; }
+    } else {
+        pl->bytes[WFB_BUF_TIME] = e * n * b;
+        pl->bytes[WFB_BUF_SPECTRUM] = e * (n + 2) * b;
+    }
+    if (!(pl->flags & WFB_PLAN_NO_DEVICE_BUFFERS))
+        for (int i = 0; i < 2; i++)
+            if (pl->bytes[i]) { if (cudaMalloc(&pl->d_buf[i], pl->bytes[i]) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; } }
+    if (!(pl->flags & WFB_PLAN_NO_HOST_BUFFERS)) {
+        if (pl->kind == WFB_R2C && pl->batch == 1) {
+            // the reference's input and output views are the same bytes (index.js:136-141)
+            if (cudaHostAlloc(&pl->h_buf[1], pl->bytes[1], cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+            memset(pl->h_buf[1], 0, pl->bytes[1]);
+            pl->h_buf[0] = pl->h_buf[1];
+            pl->host_alias = true;
+        } else {
+            for (int i = 0; i < 2; i++)
+                if (pl->bytes[i]) {
+                    if (cudaHostAlloc(&pl->h_buf[i], pl->bytes[i], cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+                    memset(pl->h_buf[i], 0, pl->bytes[i]);
+                }
+        }
+    }
+    return WFB_OK;
+}
+
+extern "C" {
+
+wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long batch, int device, int flags, int *err) {
+    int dummy;
+    if (!err) err = &dummy;
+    int lo, hi;
+    *err = wfb_size_range(kind, precision, layout, &lo, &hi);
+    if (*err) return nullptr;
+    if (!is_pow2(n) || n < lo || n > hi) { *err = WFB_ERR_BAD_SIZE; return nullptr; }
+    if (batch < 1) { *err = WFB_ERR_BAD_ARG; return nullptr; }
+    *err = check_device(device);
+    if (*err) return nullptr;
+
+    wfb_plan *pl = new wfb_plan();
+    pl->kind = kind; pl->precision = precision; pl->layout = (kind == WFB_C2C) ? layout : WFB_INTERLEAVED;
+    pl->n = n; pl->batch = batch; pl->device = device; pl->flags = flags;
+    pl->core_n = (kind == WFB_R2C) ? n / 2 : n;
+    pl->elem = precision == WFB_F64 ? 8 : 4;
+    pl->variant = 0;
+    const std::vector<Variant> &all = precision == WFB_F64 ? variants_f64() : variants_f32();
+    for (const Variant &v : all)
+        if (v.core_n == pl->core_n && pl->variants.size() < 8) pl->variants.push_back(&v);
+    if (pl->variants.empty()) { *err = WFB_ERR_BAD_SIZE; delete pl; return nullptr; }
+    *err = plan_init(pl);
+    if (*err) { wfb_plan_destroy(pl); return nullptr; }
+    return pl;
+}
+
+wfb_plan *wfb_plan_create(int kind, int precision, int layout, int n, long batch, int device, int *err) {
+    return wfb_plan_create_ex(kind, precision, layout, n, batch, device, 0, err);
+}
+
+void wfb_plan_destroy(wfb_plan *pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    if (pl->stream) { cudaStreamSynchronize(pl->stream); cudaStreamDestroy(pl->stream); }
+    for (int i = 0; i < 8; i++) { if (pl->d_tw_fwd[i]) cudaFree(pl->d_tw_fwd[i]); if (pl->d_tw_inv[i]) cudaFree(pl->d_tw_inv[i]); }
+    if (pl->d_rtw) cudaFree(pl->d_rtw);
+    for (int i = 0; i < 2; i++) if (pl->d_buf[i]) cudaFree(pl->d_buf[i]);
+    if (pl->host_alias) { if (pl->h_buf[1]) cudaFreeHost(pl->h_buf[1]); }
+    else for (int i = 0; i < 2; i++) if (pl->h_buf[i]) cudaFreeHost(pl->h_buf[i]);
+    delete pl;
+}
+
+void *wfb_host_buffer(wfb_plan *pl, int which) { return (pl && which >= 0 && which < 2) ? pl->h_buf[which] : nullptr; }
+void *wfb_device_buffer(wfb_plan *pl, int which) { return (pl && which >= 0 && which < 2) ? pl->d_buf[which] : nullptr; }
+size_t wfb_host_bytes(wfb_plan *pl, int which) { return (pl && which >= 0 && which < 2) ? pl->bytes[which] : 0; }
+// C2C contexts are in place: the input view is the output view (index.js:78-83)
+void *wfb_host_in(wfb_plan *pl, int plane) { return wfb_host_buffer(pl, plane); }
+void *wfb_host_out(wfb_plan *pl, int plane) { return wfb_host_buffer(pl, plane); }
+void *wfb_plan_stream(wfb_plan *pl) { return pl ? (void *)pl->stream : nullptr; }
+
+int wfb_plan_variant_count(wfb_plan *pl) { return pl ? (int)pl->variants.size() : 0; }
+int wfb_plan_set_variant(wfb_plan *pl, int v) {
+    if (!pl || v < 0 || v >= (int)pl->variants.size()) return WFB_ERR_BAD_ARG;
+    pl->variant = v;
+    return WFB_OK;
+}
+const char *wfb_plan_variant_name(wfb_plan *pl, int v) {
+    if (!pl || v < 0 || v >= (int)pl->variants.size()) return "";
+    return pl->variants[v]->name;
+}
+size_t wfb_plan_algorithmic_bytes(wfb_plan *pl) {
+    if (!pl) return 0;
+    const size_t e = pl->elem, n = (size_t)pl->n, b = (size_t)pl->batch;
+    if (pl->kind == WFB_C2C) return 2 * (2 * e * n) * b;          // one read + one write of n complex values
+    return (e * n + e * (n + 2)) * b;                               // n reals one way, n/2+1 bins the other
+}
+unsigned long long wfb_kernel_launch_count(void) { return g_launches.load(); }
+
+int wfb_exec_device(wfb_plan *pl, int direction, const void *const d_in[2], void *const d_out[2], void *stream) {
+    if (!pl || !d_in || !d_out || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
+    CK(cudaSetDevice(pl->device));
+    const Variant &v = *pl->variants[pl->variant];
+    cudaStream_t s = stream ? (cudaStream_t)stream : pl->stream;
+    KParams p;
+    p.in0 = d_in[0]; p.in1 = d_in[1]; p.out0 = d_out[0]; p.out1 = d_out[1];
+    p.tw = direction == WFB_INVERSE ? pl->d_tw_inv[pl->variant] : pl->d_tw_fwd[pl->variant];
+    p.rtw = pl->d_rtw;
+    p.batch = pl->batch;
+    p.scale = 1.0 / (double)pl->n;
+    cudaError_t e;
+    if (pl->kind == WFB_C2C) {
+        if (!p.in0 || !p.out0 || (pl->layout == WFB_SPLIT && (!p.in1 || !p.out1))) return WFB_ERR_BAD_ARG;
+        e = v.c2c(pl->layout == WFB_SPLIT ? IO_SPLIT : IO_INTERLEAVED, direction, p, pl->batch, s);
+    } else {
+        if (!p.in0 || !p.out0) return WFB_ERR_BAD_ARG;
+        if (pl->batch > 1 && p.in0 == p.out0) return WFB_ERR_BAD_ARG;   // strides differ: rows would overlap
+        e = direction == WFB_FORWARD ? v.r2c(0, 0, p, pl->batch, s) : v.c2r(0, 1, p, pl->batch, s);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return WFB_OK;
+}
+
+int wfb_sync(wfb_plan *pl) {
+    if (!pl) return WFB_ERR_BAD_ARG;
+    CK(cudaSetDevice(pl->device));
+    CK(cudaStreamSynchronize(pl->stream));
+    return WFB_OK;
+}
+
+int wfb_exec(wfb_plan *pl, int direction, int flags) {
+    if (!pl || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
+    if (!pl->d_buf[0]) return WFB_ERR_BAD_ARG;
+    if ((flags & (WFB_STAGE_H2D | WFB_STAGE_D2H)) && !pl->h_buf[0] && !pl->h_buf[1]) return WFB_ERR_NO_HOST_BUFFERS;
+    CK(cudaSetDevice(pl->device));
+    const void *in[2];
+    void *out[2];
+    int src[2] = {-1, -1}, dst[2] = {-1, -1};    // buffer ids to stage in / out
+    if (pl->kind == WFB_C2C) {
+        in[0] = out[0] = pl->d_buf[0]; in[1] = out[1] = pl->d_buf[1];
+        src[0] = dst[0] = 0;
+        if (pl->layout == WFB_SPLIT) src[1] = dst[1] = 1;
+    } else {
+        const int a = direction == WFB_FORWARD ? WFB_BUF_TIME : WFB_BUF_SPECTRUM;
+        const int b = direction == WFB_FORWARD ? WFB_BUF_SPECTRUM : WFB_BUF_TIME;
+        in[0] = pl->d_buf[a]; out[0] = pl->d_buf[b]; in[1] = nullptr; out[1] = nullptr;
+        src[0] = a; dst[0] = b;
+    }
+    if (flags & WFB_STAGE_H2D)
+        for (int i = 0; i < 2; i++)
+            if (src[i] >= 0) CK(cudaMemcpyAsync(pl->d_buf[src[i]], pl->h_buf[src[i]], pl->bytes[src[i]], cudaMemcpyHostToDevice, pl->stream));
+    int rc = wfb_exec_device(pl, direction, in, out, nullptr);
+    if (rc) return rc;
+    if (flags & WFB_STAGE_D2H)
+        for (int i = 0; i < 2; i++)
+            if (dst[i] >= 0) CK(cudaMemcpyAsync(pl->h_buf[dst[i]], pl->d_buf[dst[i]], pl->bytes[dst[i]], cudaMemcpyDeviceToHost, pl->stream));
+    if (flags & WFB_SYNC) CK(cudaStreamSynchronize(pl->stream));
+    return WFB_OK;
+}
+
+}  // extern "C"
