@@ -1,0 +1,117 @@
+"""CPU-side checks of the boundary: the library loads, exports exactly the symbols
+include/watfft_b200.h declares, validates sizes without a GPU, builds reference-exact twiddles,
+and refuses to run without a B200 (no CPU fallback)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "watfft_b200.h").read_text()
+
+
+def declared_symbols():
+    return sorted(set(re.findall(r"WFB_API\s+[\w\s\*]+?\b(wfb_\w+)\s*\(", HEADER)))
+
+
+def test_header_and_binding_agree(wf):
+    decl = declared_symbols()
+    assert len(decl) >= 20
+    assert sorted(wf._cabi.SYMBOLS) == decl
+
+
+def test_library_exports_every_declared_symbol(wf):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", str(wf._cabi.LIB_PATH)], text=True)
+    exported = set(re.findall(r"\sT\s+(wfb_\w+)", out))
+    assert set(declared_symbols()) <= exported
+    lib = wf._cabi.lib()
+    for name in declared_symbols():
+        assert getattr(lib, name)
+    # nothing from the oracle is linked into the product
+    assert "wfo_" not in out and "watref_" not in out
+
+
+def test_size_ranges(wf):
+    C = wf._cabi
+    lib = C.lib()
+    lo, hi = ctypes.c_int(), ctypes.c_int()
+    assert lib.wfb_size_range(C.C2C, C.F32, C.SPLIT, lo, hi) == 0 and (lo.value, hi.value) == (4, 8192)
+    assert lib.wfb_size_range(C.C2C, C.F32, C.INTERLEAVED, lo, hi) == 0 and (lo.value, hi.value) == (4, 8192)
+    assert lib.wfb_size_range(C.R2C, C.F32, 0, lo, hi) == 0 and (lo.value, hi.value) == (32, 16384)
+    assert lib.wfb_size_range(C.C2C, C.F64, C.INTERLEAVED, lo, hi) == 0
+    assert lib.wfb_size_range(C.C2C, C.F64, C.SPLIT, lo, hi) == C.ERR_UNSUPPORTED
+    assert lib.wfb_size_range(7, C.F32, 0, lo, hi) == C.ERR_UNSUPPORTED
+
+
+def test_strerror_covers_codes(wf):
+    lib = wf._cabi.lib()
+    msgs = {lib.wfb_strerror(c).decode() for c in range(0, -8, -1)}
+    assert len(msgs) == 8 and "no CPU fallback" in lib.wfb_strerror(-1).decode()
+
+
+def test_plan_validation_order(wf):
+    """Bad sizes are rejected before the device is touched, so this holds with or without a GPU."""
+    C = wf._cabi
+    for n in (0, 3, 12, 1000, 2, 16384):
+        with pytest.raises(wf.WatFFTError) as e:
+            wf.Plan(C.C2C, C.F32, C.SPLIT, n)
+        assert e.value.code == C.ERR_BAD_SIZE
+    with pytest.raises(wf.WatFFTError) as e:
+        wf.Plan(C.R2C, C.F32, 0, 16)          # rfft_split needs n >= 32
+    assert e.value.code == C.ERR_BAD_SIZE
+    with pytest.raises(wf.WatFFTError) as e:
+        wf.Plan(C.C2C, C.F32, C.SPLIT, 64, batch=0)
+    assert e.value.code == C.ERR_BAD_ARG
+
+
+def test_no_cpu_fallback(wf):
+    """Without a B200 every factory throws WFB_ERR_NO_DEVICE (north_star: the GPU context throws)."""
+    lib = wf._cabi.lib()
+    if lib.wfb_device_count() > 0 and lib.wfb_require_b200(0) == 0:
+        pytest.skip("a B200 is present")
+    for factory in (wf.createFFT, wf.createFFTf32, wf.createRFFT, wf.createRFFTf32, wf.createFFTf32Split):
+        with pytest.raises(wf.WatFFTError) as e:
+            factory(1024)
+        assert e.value.code == wf._cabi.ERR_NO_DEVICE
+    assert lib.wfb_kernel_launch_count() == 0
+
+
+@pytest.mark.parametrize("n", [8, 16, 64, 1024, 4096, 8192])
+def test_product_twiddles_bit_exact_with_oracle(wf, oracle, n):
+    """The product's own host trig (csrc/wfb_twiddle.h) must reproduce the reference tables bit for bit;
+    the oracle's tables are themselves pinned to the reference modules (test_oracle_pinning.py)."""
+    lib = wf._cabi.lib()
+    for flavour, kind, dt in ((0, "split", np.float32), (1, "dual", np.float32), (2, "f64", np.float64)):
+        re, im = np.zeros(n, dt), np.zeros(n, dt)
+        assert lib.wfb_reference_twiddles(flavour, n, n, re.ctypes.data, im.ctypes.data) == 0
+        ore, oim = oracle.twiddles(kind, n)
+        assert np.array_equal(re, ore) and np.array_equal(im, oim), (kind, n)
+
+
+def test_twiddle_tables_match_reference_module_memory(wf, watref):
+    """...and directly against the bytes the reference's precompute export writes."""
+    lib = wf._cabi.lib()
+    n = 1024
+    watref.call("fft_split_native_f32", "precompute_twiddles_split", n)
+    ref_re = watref.view("fft_split_native_f32", np.float32, 0x20000, n).copy()
+    ref_im = watref.view("fft_split_native_f32", np.float32, 0x28000, n).copy()
+    re, im = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    lib.wfb_reference_twiddles(0, n, n, re.ctypes.data, im.ctypes.data)
+    assert np.array_equal(re, ref_re) and np.array_equal(im, ref_im)
+    watref.call("fft_combined", "precompute_twiddles", n)
+    t = watref.view("fft_combined", np.float64, 262144, 2 * n).copy()
+    re, im = np.zeros(n), np.zeros(n)
+    lib.wfb_reference_twiddles(2, n, n, re.ctypes.data, im.ctypes.data)
+    assert np.array_equal(re, t[0::2]) and np.array_equal(im, t[1::2])
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under wat-fft_b200/ may reference it."""
+    for p in (ROOT / "wat-fft_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".cc", ".js", ".mjs") and p.is_file():
+            text = p.read_text(errors="ignore")
+            assert "libwatfft_oracle" not in text and "watfft_oracle.c" not in text and "libwatref" not in text, p
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), p

@@ -1,0 +1,172 @@
+"""GPU engine vs the committed reference-module outputs (tests/golden/watref_vectors.npz) and the
+size-independent properties of the domain at BASELINE.json's full batch sizes."""
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle as om
+from conftest import f32_bound, f64_bound, rel_err
+
+pytestmark = pytest.mark.gpu
+FIX = np.load(Path(__file__).resolve().parent / "golden" / "watref_vectors.npz")
+FIX_SIZES = [4, 8, 16, 32, 64, 128, 256, 1024, 4096]
+
+
+@pytest.mark.parametrize("n", FIX_SIZES)
+def test_gpu_vs_reference_module_fixtures(wf, n):
+    re, im, xr = FIX[f"in_re_{n}"], FIX[f"in_im_{n}"], FIX[f"in_real_{n}"]
+    xin = np.r_[re, im]
+    for inv, tag in ((False, "fwd"), (True, "inv")):
+        c = wf.createFFTf32Split(n)
+        c.getRealBuffer()[:] = re
+        c.getImagBuffer()[:] = im
+        c.inverse() if inv else c.forward()
+        got = np.r_[c.getRealBuffer(), c.getImagBuffer()]
+        c.dispose()
+        assert rel_err(got, np.r_[FIX[f"split_{tag}_re_{n}"], FIX[f"split_{tag}_im_{n}"]], xin) <= f32_bound(n)
+        x = np.empty(2 * n, np.float32)
+        x[0::2], x[1::2] = re, im
+        c = wf.createFFTf32(n)
+        c.getInputBuffer()[:] = x
+        c.inverse() if inv else c.forward()
+        assert rel_err(c.getOutputBuffer(), FIX[f"dual_{tag}_{n}"], x) <= f32_bound(n)
+        c.dispose()
+        d = np.empty(2 * n)
+        d[0::2], d[1::2] = om.lcg_signal(n, 12345 + n), om.lcg_signal(n, 54321 + n)
+        c = wf.createFFT(n)
+        c.getInputBuffer()[:] = d
+        c.inverse() if inv else c.forward()
+        assert rel_err(c.getOutputBuffer(), FIX[f"f64_{tag}_{n}"], d) <= f64_bound(n)
+        c.dispose()
+    if n >= 32:
+        c = wf.createRFFTf32(n)
+        c.getInputBuffer()[:] = xr.astype(np.float32)
+        c.forward()
+        assert rel_err(c.getOutputBuffer(), FIX[f"rfft32_{n}"], xr) <= f32_bound(n)
+        c.getOutputBuffer()[:] = FIX[f"rfft32_{n}"]
+        c.inverse()
+        assert rel_err(c.getInputBuffer(), FIX[f"irfft32_{n}"], FIX[f"rfft32_{n}"]) <= f32_bound(n)
+        c.dispose()
+    if n >= 8:
+        c = wf.createRFFT(n)
+        c.getInputBuffer()[:] = xr
+        c.forward()
+        assert rel_err(c.getOutputBuffer(), FIX[f"rfft64_{n}"], xr) <= f64_bound(n)
+        c.dispose()
+
+
+@pytest.mark.parametrize("n", [16, 256, 4096])
+def test_full_size_properties_c2c(wf, oracle, n):
+    """BASELINE config 2 at full size (1 GiB of input): rows checked against the oracle on a sample,
+    linearity, and the fft->ifft round trip over the WHOLE batch."""
+    import torch
+    C = wf._cabi
+    batch = (1 << 30) // (8 * n)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(n)
+    re = torch.rand(batch * n, device=dev, generator=g) * 2 - 1
+    im = torch.rand(batch * n, device=dev, generator=g) * 2 - 1
+    ore, oim = torch.empty_like(re), torch.empty_like(im)
+    plan = wf.Plan(C.C2C, C.F32, C.SPLIT, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    plan.exec_device(C.FORWARD, (re.data_ptr(), im.data_ptr()), (ore.data_ptr(), oim.data_ptr()))
+    plan.sync()
+    for r in sorted({0, 1, batch // 2, batch - 1}):
+        a, b = re[r * n:(r + 1) * n].cpu().numpy(), im[r * n:(r + 1) * n].cpu().numpy()
+        er, ei = oracle.fft_split_f32(a, b)
+        got = np.r_[ore[r * n:(r + 1) * n].cpu().numpy(), oim[r * n:(r + 1) * n].cpu().numpy()]
+        assert rel_err(got, np.r_[er, ei], np.r_[a, b]) <= f32_bound(n), (n, r)
+    # Parseval over the whole batch: sum |X|^2 = N * sum |x|^2
+    e_t = float((re.double() ** 2).sum() + (im.double() ** 2).sum())
+    e_f = float((ore.double() ** 2).sum() + (oim.double() ** 2).sum())
+    assert abs(e_f / (n * e_t) - 1) < 1e-5
+    # round trip in place over the whole batch
+    plan.exec_device(C.INVERSE, (ore.data_ptr(), oim.data_ptr()), (ore.data_ptr(), oim.data_ptr()))
+    plan.sync()
+    assert float((ore - re).abs().max()) < 1e-4 and float((oim - im).abs().max()) < 1e-4
+    plan.destroy()
+
+
+@pytest.mark.parametrize("n", [64, 4096])
+def test_full_size_properties_r2c(wf, oracle, n):
+    import torch
+    C = wf._cabi
+    batch = (1 << 30) // (4 * n)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(n)
+    x = torch.rand(batch * n, device=dev, generator=g) * 2 - 1
+    spec = torch.empty(batch * (n + 2), device=dev)
+    back = torch.empty_like(x)
+    plan = wf.Plan(C.R2C, C.F32, 0, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
+    plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))
+    plan.sync()
+    for r in sorted({0, batch // 2, batch - 1}):
+        a = x[r * n:(r + 1) * n].cpu().numpy()
+        got = spec[r * (n + 2):(r + 1) * (n + 2)].cpu().numpy()
+        assert rel_err(got, oracle.rfft_split_f32(a), a) <= f32_bound(n), (n, r)
+    assert float((back - x).abs().max()) < 1e-4          # irfft(rfft(x)) = x over the whole batch
+    plan.destroy()
+
+
+def test_sharded_context_single_device(wf):
+    from watfft_b200.sharding import ShardedSplitFFT
+    n, batch = 256, 19
+    rng = np.random.default_rng(3)
+    re = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    im = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    sh = ShardedSplitFFT(n, batch, devices=[0, 0, 0])     # three shards on one device: same code path
+    sh.scatter(re, im)
+    sh.run()
+    gr, gi = sh.gather()
+    sh.dispose()
+    truth = np.fft.fft(re.astype(np.float64) + 1j * im, axis=-1)
+    assert np.max(np.abs((gr + 1j * gi) - truth)) < 5e-3
+
+
+def test_context_contract(wf):
+    """Buffer lengths / aliasing per index.js:73-83,131-141; batch rows are independent."""
+    n = 64
+    c = wf.createFFTf32(n)
+    assert c.getInputBuffer().size == 2 * n and c.getInputBuffer().ctypes.data == c.getOutputBuffer().ctypes.data
+    c.dispose()
+    r = wf.createRFFTf32(n)
+    assert r.getInputBuffer().size == n and r.getOutputBuffer().size == n + 2
+    assert r.getInputBuffer().ctypes.data == r.getOutputBuffer().ctypes.data       # same bytes at batch = 1
+    r.dispose()
+    rb = wf.createRFFTf32(n, batch=3)
+    assert rb.getInputBuffer().size == 3 * n and rb.getOutputBuffer().size == 3 * (n + 2)
+    rb.dispose()
+    # row independence: changing row 1 must not change row 0's output
+    x = np.random.default_rng(0).uniform(-1, 1, (2, 2 * n)).astype(np.float32)
+    c2 = wf.createFFTf32(n, batch=2)
+    c2.getInputBuffer()[:] = x.ravel()
+    c2.forward()
+    first = c2.getOutputBuffer().reshape(2, -1)[0].copy()
+    x[1] = 0
+    c2.getInputBuffer()[:] = x.ravel()
+    c2.forward()
+    assert np.array_equal(first, c2.getOutputBuffer().reshape(2, -1)[0])
+    assert np.all(c2.getOutputBuffer().reshape(2, -1)[1] == 0)
+    c2.dispose()
+
+
+def test_exports_facade(wf):
+    """The exports-shaped facade runs the reference's raw-export call sequence unchanged."""
+    ex = wf.SplitExportsFacade("fft_split_native_f32")
+    n = 1024
+    re = np.frombuffer(ex.memory, np.float32, n, ex.REAL_OFFSET)
+    im = np.frombuffer(ex.memory, np.float32, n, ex.IMAG_OFFSET)
+    rng = np.random.default_rng(1)
+    a, b = rng.uniform(-1, 1, n).astype(np.float32), rng.uniform(-1, 1, n).astype(np.float32)
+    re[:], im[:] = a, b
+    ex.precompute_twiddles_split(n)
+    ex.fft_split(n)
+    truth = np.fft.fft(a.astype(np.float64) + 1j * b)
+    assert np.max(np.abs((re + 1j * im) - truth)) < 5e-3
+    ex.ifft_split(n)
+    assert np.max(np.abs(re - a)) < 1e-4
+    ex.dispose()

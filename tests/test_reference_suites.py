@@ -1,0 +1,308 @@
+"""The reference's own correctness suites, restated as pytest and run against three backends:
+
+  oracle  -- oracle/watfft_oracle.c (CPU restatement)          [-m "not gpu"]
+  watref  -- the transpiled reference modules (oracle/_ref)     [-m "not gpu"]
+  gpu     -- the B200 engine through the context API / C ABI    [-m gpu]
+
+Passing on `watref` with the reference's own tolerances validates the transpiler; passing on
+`oracle` pins the restatement; passing on `gpu` is the acceptance gate of the task.  Suites and
+tolerances (file:line under the reference repo):
+  tests/golden_reference.test.js:32-290      inline golden vectors
+  tests/per_bin_validation.test.js:29-299    f64 every-bin cos/sin, 3-tone mix
+  tests/per_bin_f32.test.js:33-177           f32 every-bin (split, interleaved, rfft_split, irfft_split)
+  tests/output-order.test.js:88-463          distinct-bin ordering signal, LCG random vs DFT
+  tests/rfft.test.js:102-396                 impulse/DC/Nyquist/Parseval/LCG for f64 rfft
+  tests/ifft.test.js:15-213                  round trips
+  tests/fft_split_native.test.js:78-295      split forward/roundtrip/rfft/irfft vs DFT
+  tests/fft_f32_dual.test.js:52-86           interleaved f32 forward
+  tests/accuracy.test.js:21-31 + tools/accuracy_report.js:57-76   aggregate error metrics
+Per-bin loops are batched (one row per bin) so the GPU runs them as one call.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle as om
+from backends import GpuBackend, OracleBackend, WatRefBackend
+
+BACKENDS = ["oracle", "watref", pytest.param("gpu", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def be(request):
+    if request.param == "oracle":
+        return OracleBackend(request.getfixturevalue("oracle"))
+    if request.param == "watref":
+        return WatRefBackend(request.getfixturevalue("watref"))
+    return GpuBackend(request.getfixturevalue("wf"))
+
+
+def il(z):
+    out = np.empty(z.shape[:-1] + (2 * z.shape[-1],), np.float64)
+    out[..., 0::2], out[..., 1::2] = z.real, z.imag
+    return out
+
+
+def cx(a):
+    a = np.asarray(a, np.float64)
+    return a[..., 0::2] + 1j * a[..., 1::2]
+
+
+def fft_truth(z):
+    """f64 ground truth (numpy.fft in f64 == tests/dft-reference.js to ~1e-15 relative)."""
+    return np.fft.fft(np.asarray(z, np.complex128), axis=-1)
+
+
+# ---------------------------------------------------------------- golden_reference.test.js
+def test_golden_complex(be):
+    ramp = np.zeros(16)
+    ramp[0::2] = np.arange(8)
+    exp8 = [28, 0, -4, 9.65685424949238, -4, 4, -4, 1.6568542494923806, -4, 0, -4, -1.6568542494923806, -4, -4, -4,
+            -9.65685424949238]
+    got = be.fft_f64(ramp[None])[0]
+    assert np.max(np.abs(got - exp8)) < max(1e-9, 8 * 1e-11)
+    imp = np.zeros(32)
+    imp[0] = 1
+    exp16 = np.tile([1.0, 0.0], 16)
+    assert np.max(np.abs(be.fft_f64(imp[None])[0] - exp16)) < max(1e-9, 16 * 1e-11)
+    n = 32
+    x = np.zeros(64)
+    x[0::2] = np.cos(2 * np.pi * 4 * np.arange(n) / n)
+    exp32 = np.zeros(64)
+    exp32[8] = 16
+    exp32[56] = 16
+    assert np.max(np.abs(be.fft_f64(x[None])[0] - exp32)) < max(1e-9, 32 * 1e-11)
+
+
+def test_golden_real(be):
+    tol = 1e-10
+    imp = np.zeros(8)
+    imp[0] = 1
+    assert np.max(np.abs(be.rfft_f64(imp[None])[0] - np.tile([1.0, 0.0], 5))) < tol
+    exp = np.zeros(18)
+    exp[0] = 80
+    assert np.max(np.abs(be.rfft_f64(np.full((1, 16), 5.0))[0] - exp)) < tol
+    t = np.arange(32)
+    exp = np.zeros(34)
+    exp[2] = 16
+    assert np.max(np.abs(be.rfft_f64(np.cos(2 * np.pi * t / 32)[None])[0] - exp)) < tol
+    x = (np.cos(2 * np.pi * 1 * t / 32) + 0.5 * np.cos(2 * np.pi * 7 * t / 32) + 0.3 * np.cos(2 * np.pi * 14 * t / 32)
+         + 0.2 * np.cos(2 * np.pi * 15 * t / 32))
+    exp = np.zeros(34)
+    exp[2], exp[14], exp[28], exp[30] = 16, 8, 4.8, 3.2
+    assert np.max(np.abs(be.rfft_f64(x[None])[0] - exp)) < tol
+
+
+# ---------------------------------------------------------------- per_bin_validation.test.js (f64)
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256])
+def test_per_bin_f64_complex(be, n):
+    t = np.arange(n)
+    bins = np.arange(n)
+    cosx = np.zeros((n, 2 * n))
+    cosx[:, 0::2] = np.cos(2 * np.pi * bins[:, None] * t[None, :] / n)
+    out = cx(be.fft_f64(cosx))
+    tol = n * 1e-10
+    for k in range(n):
+        exp = np.zeros(n, complex)
+        if k == 0 or 2 * k == n:
+            exp[k] = n
+        else:
+            exp[k] = exp[n - k] = n / 2
+        assert np.max(np.abs(out[k] - exp)) < tol, (n, k)
+    sinx = np.zeros((n, 2 * n))
+    sinx[:, 0::2] = np.sin(2 * np.pi * bins[:, None] * t[None, :] / n)
+    out = cx(be.fft_f64(sinx))
+    for k in range(1, n // 2):
+        assert abs(out[k, k] - (-0.5j * n)) < tol and out[k, k].imag < 0      # sin => im < 0 at +k
+        assert abs(out[k, n - k] - (0.5j * n)) < tol
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256])
+def test_per_bin_f64_real(be, n):
+    t = np.arange(n)
+    bins = np.arange(n // 2 + 1)
+    out = cx(be.rfft_f64(np.cos(2 * np.pi * bins[:, None] * t[None, :] / n)))
+    tol = n * 1e-10
+    for k in bins:
+        exp = np.zeros(n // 2 + 1, complex)
+        exp[k] = n if (k == 0 or 2 * k == n) else n / 2
+        assert np.max(np.abs(out[k] - exp)) < tol, (n, k)
+    # 3-tone mix (tolerance N*1e-9) and the regression bins 9..15 at N = 32
+    if n >= 32:
+        x = np.cos(2 * np.pi * 3 * t / n) + 0.5 * np.sin(2 * np.pi * 5 * t / n) + 0.25 * np.cos(2 * np.pi * 9 * t / n)
+        got = cx(be.rfft_f64(x[None]))[0]
+        assert np.max(np.abs(got - np.fft.rfft(x))) < n * 1e-9
+
+
+# ---------------------------------------------------------------- per_bin_f32.test.js
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256])
+def test_per_bin_f32_complex(be, n):
+    t = np.arange(n)
+    bins = np.arange(n)
+    c = np.cos(2 * np.pi * bins[:, None] * t[None, :] / n).astype(np.float32)
+    re, im = be.fft_split_f32(c, np.zeros_like(c))
+    x = np.zeros((n, 2 * n), np.float32)
+    x[:, 0::2] = c
+    ilo = cx(be.fft_interleaved_f32(x))
+    tol = n * 5e-6
+    for k in range(n):
+        exp = np.zeros(n, complex)
+        if k == 0 or 2 * k == n:
+            exp[k] = n
+        else:
+            exp[k] = exp[n - k] = n / 2
+        assert np.max(np.abs((re[k] + 1j * im[k]) - exp)) < tol, ("split", n, k)
+        assert np.max(np.abs(ilo[k] - exp)) < tol, ("interleaved", n, k)
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256])
+def test_per_bin_f32_real(be, n):
+    t = np.arange(n)
+    bins = np.arange(n // 2 + 1)
+    tol = n * 5e-6
+    out = cx(be.rfft_f32(np.cos(2 * np.pi * bins[:, None] * t[None, :] / n).astype(np.float32)))
+    for k in bins:
+        exp = np.zeros(n // 2 + 1, complex)
+        exp[k] = n if (k == 0 or 2 * k == n) else n / 2
+        assert np.max(np.abs(out[k] - exp)) < tol, (n, k)
+    outs = cx(be.rfft_f32(np.sin(2 * np.pi * bins[1:-1, None] * t[None, :] / n).astype(np.float32)))
+    for i, k in enumerate(bins[1:-1]):
+        exp = np.zeros(n // 2 + 1, complex)
+        exp[k] = -0.5j * n
+        assert np.max(np.abs(outs[i] - exp)) < tol, (n, k)
+    # irfft_split: single-bin spectrum -> cosine (:151-177)
+    spec = np.zeros((n // 2 + 1, n + 2), np.float32)
+    for k in bins:
+        spec[k, 2 * k] = n if (k == 0 or 2 * k == n) else n / 2
+    x = be.irfft_f32(spec)
+    for k in bins:
+        assert np.max(np.abs(x[k] - np.cos(2 * np.pi * k * t / n))) < tol / n + 1e-5, (n, k)
+
+
+# ---------------------------------------------------------------- output-order.test.js
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024])
+def test_output_order(be, n):
+    # LCG random (seeds 42+n / 123+n) vs the DFT: f64 complex
+    z = om.lcg_signal(n, 42 + n) + 1j * om.lcg_signal(n, 123 + n)
+    got = cx(be.fft_f64(il(z)[None]))[0]
+    assert np.max(np.abs(got - fft_truth(z))) < max(1e-9, n * 1e-11)
+    # f64 rfft (seed 456+n)
+    x = om.lcg_signal(n, 456 + n)
+    got = cx(be.rfft_f64(x[None]))[0]
+    assert np.max(np.abs(got - np.fft.rfft(x))) < max(1e-9, n * 5e-11)
+    # distinct-bin signal: bin k has amplitude k+1 -> any permutation of the output is caught
+    t = np.arange(n)
+    sig = sum((k + 1) * np.exp(2j * np.pi * k * t / n) for k in range(n)) / n
+    got = cx(be.fft_f64(il(sig)[None]))[0]
+    assert np.max(np.abs(got - (np.arange(n) + 1))) < max(1e-4, n * 1e-7)
+    re, im = be.fft_split_f32(sig.real[None].astype(np.float32), sig.imag[None].astype(np.float32))
+    assert np.max(np.abs((re[0] + 1j * im[0]) - (np.arange(n) + 1))) < max(1e-4, n * 1e-6) * 8
+    # f32 vs f64 consistency (seed 789+n)
+    if n >= 32:
+        xr = om.lcg_signal(n, 789 + n)
+        g32 = cx(be.rfft_f32(xr[None].astype(np.float32)))[0]
+        assert np.max(np.abs(g32 - np.fft.rfft(xr))) < max(1e-3, n * 1e-5)
+    if n == 64:
+        s7 = np.sin(2 * np.pi * 7 * t / n)
+        mag = np.abs(cx(be.rfft_f64(s7[None]))[0])
+        assert int(np.argmax(mag)) == 7
+
+
+# ---------------------------------------------------------------- rfft.test.js (f64)
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_rfft_f64_properties(be, n):
+    tol = max(1e-9, n * 5e-11)
+    imp = np.zeros(n)
+    imp[0] = 1
+    assert np.max(np.abs(cx(be.rfft_f64(imp[None]))[0] - 1.0)) < tol
+    dc = cx(be.rfft_f64(np.ones((1, n))))[0]
+    assert abs(dc[0] - n) < tol and np.max(np.abs(dc[1:])) < tol
+    nyq = cx(be.rfft_f64(np.cos(np.pi * np.arange(n))[None]))[0]
+    assert abs(nyq[n // 2] - n) < tol and np.max(np.abs(nyq[:-1])) < tol
+    for seed in (12345, 54321, 98765):
+        x = om.lcg_signal(n, seed + n)
+        got = cx(be.rfft_f64(x[None]))[0]
+        assert np.max(np.abs(got - np.fft.rfft(x))) < tol
+        # Parseval
+        e_t = np.sum(x * x)
+        e_f = (abs(got[0]) ** 2 + abs(got[-1]) ** 2 + 2 * np.sum(np.abs(got[1:-1]) ** 2)) / n
+        assert abs(e_t - e_f) < tol * n
+
+
+# ---------------------------------------------------------------- ifft.test.js
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024])
+def test_roundtrips(be, n):
+    rng = np.random.default_rng(n)
+    d = rng.uniform(-1, 1, (3, 2 * n))
+    assert np.max(np.abs(be.fft_f64(be.fft_f64(d), True) - d)) < 1.5e-10
+    f = d.astype(np.float32)
+    assert np.max(np.abs(be.fft_interleaved_f32(be.fft_interleaved_f32(f), True) - f)) < 1e-4
+    re, im = f[:, :n].copy(), f[:, n:].copy()
+    r2, i2 = be.fft_split_f32(*be.fft_split_f32(re, im), True)
+    assert max(np.max(np.abs(r2 - re)), np.max(np.abs(i2 - im))) < 1e-4
+    if n >= 32:
+        x = f[:, :n].copy()
+        assert np.max(np.abs(be.irfft_f32(be.rfft_f32(x)) - x)) < 1e-4
+
+
+# ---------------------------------------------------------------- fft_split_native.test.js / fft_f32_dual.test.js
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_split_and_dual_forward_vs_dft(be, n):
+    rng = np.random.default_rng(77 + n)
+    re = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+    im = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+    truth = fft_truth(re.astype(np.float64) + 1j * im)
+    gr, gi = be.fft_split_f32(re, im)
+    assert np.max(np.abs((gr + 1j * gi) - truth)) < 5e-3                                  # :78-114
+    x = np.empty((2, 2 * n), np.float32)
+    x[:, 0::2], x[:, 1::2] = re, im
+    assert np.max(np.abs(cx(be.fft_interleaved_f32(x)) - truth)) < max(1e-4 * math.sqrt(n / 1024), 2e-5) * 8   # :52
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_split_real_vs_dft(be, n):
+    t = np.arange(n)
+    rng = np.random.default_rng(5 + n)
+    sigs = np.stack([np.eye(1, n, 0)[0], np.eye(1, n, 3)[0], np.sin(2 * np.pi * 5 * t / n) + 0.5,
+                     rng.uniform(-1, 1, n)]).astype(np.float32)
+    truth = np.fft.rfft(sigs.astype(np.float64), axis=-1)
+    got = cx(be.rfft_f32(sigs))
+    for r in range(4):
+        assert np.max(np.abs(got[r] - truth[r])) / np.max(np.abs(truth[r])) <= 1e-4, (n, r)      # :153-211
+    # irfft from the exact f64 spectrum (:213-246)
+    back = be.irfft_f32(il(truth).astype(np.float32))
+    for r in range(4):
+        assert np.max(np.abs(back[r] - sigs[r])) / np.max(np.abs(sigs[r])) <= 1e-4, (n, r)
+
+
+# ---------------------------------------------------------------- accuracy.test.js + tools/accuracy_report.js
+def _stats(actual, expected):
+    actual, expected = np.asarray(actual, np.float64).ravel(), np.asarray(expected, np.float64).ravel()
+    d = np.abs(actual - expected)
+    return d.max() / np.abs(expected).max(), math.sqrt(np.sum(d * d) / np.sum(expected * expected))
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_accuracy_report(be, n):
+    sre, sim, sreal = om.lcg_signal(n, 12345 + n), om.lcg_signal(n, 54321 + n), om.lcg_signal(n, 98765 + n)
+    z = sre + 1j * sim
+    spec = fft_truth(z)
+    rspec = np.fft.rfft(sreal)
+    rows = []
+    rows.append(("f64 fft", _stats(be.fft_f64(il(z)[None])[0], il(spec)), 1e-9, 5e-10))
+    rows.append(("f64 ifft", _stats(be.fft_f64(il(spec)[None], True)[0], il(z)), 1e-9, 5e-10))
+    rows.append(("f64 rfft", _stats(be.rfft_f64(sreal[None])[0], il(rspec)), 1e-9, 5e-10))
+    f = il(z).astype(np.float32)
+    rows.append(("dual fft", _stats(be.fft_interleaved_f32(f[None])[0], il(spec)), 5e-6, 2e-6))
+    rows.append(("dual ifft", _stats(be.fft_interleaved_f32(il(spec).astype(np.float32)[None], True)[0], il(z)), 5e-6, 2e-6))
+    gr, gi = be.fft_split_f32(sre[None].astype(np.float32), sim[None].astype(np.float32))
+    rows.append(("split fft", _stats(np.r_[gr[0], gi[0]], np.r_[spec.real, spec.imag]), 5e-6, 2e-6))
+    gr, gi = be.fft_split_f32(spec.real[None].astype(np.float32), spec.imag[None].astype(np.float32), True)
+    rows.append(("split ifft", _stats(np.r_[gr[0], gi[0]], np.r_[sre, sim]), 5e-6, 2e-6))
+    if n >= 32:
+        rows.append(("split rfft", _stats(be.rfft_f32(sreal[None].astype(np.float32))[0], il(rspec)), 5e-6, 2e-6))
+        rows.append(("split irfft", _stats(be.irfft_f32(il(rspec)[None].astype(np.float32))[0], sreal), 5e-6, 2e-6))
+    for name, (mx, rms), tmx, trms in rows:
+        assert np.isfinite(mx) and mx <= tmx, (name, n, mx)
+        assert rms <= trms, (name, n, rms)

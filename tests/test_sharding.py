@@ -1,0 +1,63 @@
+"""Host-side multi-GPU logic, exercised on CPU with a world_size-2 gloo group (the data path has no
+collective: ranks own disjoint contiguous row ranges; only the timing is reduced)."""
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_partition_covers_rows(wf):
+    from watfft_b200.sharding import partition
+    for batch in (0, 1, 7, 8, 262144, 262145):
+        for world in (1, 2, 3, 4, 8):
+            b = partition(batch, world)
+            assert b[0][0] == 0 and b[-1][1] == batch
+            assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+            assert partition(batch, world, world - 1) == b[-1]
+    # config 5: 262144 transforms of N=4096 over 2/4/8 GPUs
+    assert [e - s for s, e in partition(262144, 8)] == [32768] * 8
+    with pytest.raises(ValueError):
+        partition(8, 0)
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "rank.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        import torch, torch.distributed as dist
+        import numpy as np
+        import watfft_b200
+        from watfft_b200.sharding import partition, max_over_ranks
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        batch = 1001
+        b, e = partition(batch, world, rank)
+        # every rank reports the rows it owns; together they must tile [0, batch) exactly once
+        owned = torch.zeros(batch, dtype=torch.int32)
+        owned[b:e] = 1
+        dist.all_reduce(owned)
+        assert int(owned.min()) == 1 and int(owned.max()) == 1
+        # job time = max over ranks
+        t = max_over_ranks(1.0 + rank)
+        assert t == float(world)
+        # whole-job throughput the way bench.py forms it
+        rows = torch.tensor([e - b], dtype=torch.int64)
+        dist.all_reduce(rows)
+        assert int(rows.item()) == batch
+        dist.destroy_process_group()
+        print("rank", rank, "ok")
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
