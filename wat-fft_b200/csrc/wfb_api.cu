@@ -172,6 +172,11 @@ struct wfb_plan {
     size_t bytes[2];
     bool host_alias;                   // R2C batch == 1: both host views share one allocation
     cudaStream_t stream;
+    // staging pipeline: chunks of rows cycle over these streams so the H2D copy of chunk c+1, the
+    // kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex)
+    enum { NPIPE = 3 };
+    cudaStream_t pipe[NPIPE];
+    cudaEvent_t pipe_done[NPIPE], start_ev;
 };
 
 static int check_device(int device) {
@@ -291,6 +296,11 @@ static int upload_tables(wfb_plan *pl, int vi) {
 static int plan_init(wfb_plan *pl) {
     CK(cudaSetDevice(pl->device));
     CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < wfb_plan::NPIPE; i++) {
+        CK(cudaStreamCreateWithFlags(&pl->pipe[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&pl->pipe_done[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&pl->start_ev, cudaEventDisableTiming));
     for (size_t vi = 0; vi < pl->variants.size(); vi++) {
         int rc = pl->precision == WFB_F64 ? upload_tables<double>(pl, (int)vi) : upload_tables<float>(pl, (int)vi);
         if (rc) return rc;
@@ -360,6 +370,11 @@ void wfb_plan_destroy(wfb_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
     if (pl->stream) { cudaStreamSynchronize(pl->stream); cudaStreamDestroy(pl->stream); }
+    for (int i = 0; i < wfb_plan::NPIPE; i++) {
+        if (pl->pipe[i]) { cudaStreamSynchronize(pl->pipe[i]); cudaStreamDestroy(pl->pipe[i]); }
+        if (pl->pipe_done[i]) cudaEventDestroy(pl->pipe_done[i]);
+    }
+    if (pl->start_ev) cudaEventDestroy(pl->start_ev);
     for (int i = 0; i < 8; i++) { if (pl->d_tw_fwd[i]) cudaFree(pl->d_tw_fwd[i]); if (pl->d_tw_inv[i]) cudaFree(pl->d_tw_inv[i]); }
     if (pl->d_rtw) cudaFree(pl->d_rtw);
     for (int i = 0; i < 2; i++) if (pl->d_buf[i]) cudaFree(pl->d_buf[i]);
@@ -394,28 +409,36 @@ size_t wfb_plan_algorithmic_bytes(wfb_plan *pl) {
 }
 unsigned long long wfb_kernel_launch_count(void) { return g_launches.load(); }
 
+// launches the current variant over `rows` rows starting at the given plane pointers
+static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void *in1, void *out0, void *out1,
+                       long rows, cudaStream_t s) {
+    const Variant &v = *pl->variants[pl->variant];
+    KParams p;
+    p.in0 = in0; p.in1 = in1; p.out0 = out0; p.out1 = out1;
+    p.tw = direction == WFB_INVERSE ? pl->d_tw_inv[pl->variant] : pl->d_tw_fwd[pl->variant];
+    p.rtw = pl->d_rtw;
+    p.batch = rows;
+    p.scale = 1.0 / (double)pl->n;
+    cudaError_t e;
+    if (pl->kind == WFB_C2C)
+        e = v.c2c(pl->layout == WFB_SPLIT ? IO_SPLIT : IO_INTERLEAVED, direction, p, rows, s);
+    else
+        e = direction == WFB_FORWARD ? v.r2c(0, 0, p, rows, s) : v.c2r(0, 1, p, rows, s);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return WFB_OK;
+}
+
 int wfb_exec_device(wfb_plan *pl, int direction, const void *const d_in[2], void *const d_out[2], void *stream) {
     if (!pl || !d_in || !d_out || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
     CK(cudaSetDevice(pl->device));
-    const Variant &v = *pl->variants[pl->variant];
     cudaStream_t s = stream ? (cudaStream_t)stream : pl->stream;
-    KParams p;
-    p.in0 = d_in[0]; p.in1 = d_in[1]; p.out0 = d_out[0]; p.out1 = d_out[1];
-    p.tw = direction == WFB_INVERSE ? pl->d_tw_inv[pl->variant] : pl->d_tw_fwd[pl->variant];
-    p.rtw = pl->d_rtw;
-    p.batch = pl->batch;
-    p.scale = 1.0 / (double)pl->n;
-    cudaError_t e;
     if (pl->kind == WFB_C2C) {
-        if (!p.in0 || !p.out0 || (pl->layout == WFB_SPLIT && (!p.in1 || !p.out1))) return WFB_ERR_BAD_ARG;
-        e = v.c2c(pl->layout == WFB_SPLIT ? IO_SPLIT : IO_INTERLEAVED, direction, p, pl->batch, s);
+        if (!d_in[0] || !d_out[0] || (pl->layout == WFB_SPLIT && (!d_in[1] || !d_out[1]))) return WFB_ERR_BAD_ARG;
     } else {
-        if (!p.in0 || !p.out0) return WFB_ERR_BAD_ARG;
-        if (pl->batch > 1 && p.in0 == p.out0) return WFB_ERR_BAD_ARG;   // strides differ: rows would overlap
-        e = direction == WFB_FORWARD ? v.r2c(0, 0, p, pl->batch, s) : v.c2r(0, 1, p, pl->batch, s);
+        if (!d_in[0] || !d_out[0]) return WFB_ERR_BAD_ARG;
+        if (pl->batch > 1 && d_in[0] == d_out[0]) return WFB_ERR_BAD_ARG;   // strides differ: rows would overlap
     }
-    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-    return WFB_OK;
+    return launch_rows(pl, direction, d_in[0], d_in[1], d_out[0], d_out[1], pl->batch, s);
 }
 
 int wfb_sync(wfb_plan *pl) {
@@ -430,27 +453,64 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
     if (!pl->d_buf[0]) return WFB_ERR_BAD_ARG;
     if ((flags & (WFB_STAGE_H2D | WFB_STAGE_D2H)) && !pl->h_buf[0] && !pl->h_buf[1]) return WFB_ERR_NO_HOST_BUFFERS;
     CK(cudaSetDevice(pl->device));
-    const void *in[2];
-    void *out[2];
-    int src[2] = {-1, -1}, dst[2] = {-1, -1};    // buffer ids to stage in / out
+    // buffer ids and per-row byte strides of the planes read and written
+    int src[2] = {-1, -1}, dst[2] = {-1, -1};
+    size_t src_row[2] = {0, 0}, dst_row[2] = {0, 0};
+    const size_t e = pl->elem, n = (size_t)pl->n;
     if (pl->kind == WFB_C2C) {
-        in[0] = out[0] = pl->d_buf[0]; in[1] = out[1] = pl->d_buf[1];
         src[0] = dst[0] = 0;
-        if (pl->layout == WFB_SPLIT) src[1] = dst[1] = 1;
+        src_row[0] = dst_row[0] = (pl->layout == WFB_SPLIT ? 1 : 2) * e * n;
+        if (pl->layout == WFB_SPLIT) { src[1] = dst[1] = 1; src_row[1] = dst_row[1] = e * n; }
     } else {
         const int a = direction == WFB_FORWARD ? WFB_BUF_TIME : WFB_BUF_SPECTRUM;
-        const int b = direction == WFB_FORWARD ? WFB_BUF_SPECTRUM : WFB_BUF_TIME;
-        in[0] = pl->d_buf[a]; out[0] = pl->d_buf[b]; in[1] = nullptr; out[1] = nullptr;
-        src[0] = a; dst[0] = b;
+        src[0] = a; dst[0] = 1 - a;
+        src_row[0] = e * (a == WFB_BUF_TIME ? n : n + 2);
+        dst_row[0] = e * (a == WFB_BUF_TIME ? n + 2 : n);
     }
-    if (flags & WFB_STAGE_H2D)
-        for (int i = 0; i < 2; i++)
-            if (src[i] >= 0) CK(cudaMemcpyAsync(pl->d_buf[src[i]], pl->h_buf[src[i]], pl->bytes[src[i]], cudaMemcpyHostToDevice, pl->stream));
-    int rc = wfb_exec_device(pl, direction, in, out, nullptr);
-    if (rc) return rc;
-    if (flags & WFB_STAGE_D2H)
-        for (int i = 0; i < 2; i++)
-            if (dst[i] >= 0) CK(cudaMemcpyAsync(pl->h_buf[dst[i]], pl->d_buf[dst[i]], pl->bytes[dst[i]], cudaMemcpyDeviceToHost, pl->stream));
+    const bool h2d = flags & WFB_STAGE_H2D, d2h = flags & WFB_STAGE_D2H;
+    // rows per pipeline chunk: ~16 MiB of the widest plane, so each copy is long enough to run at
+    // full PCIe rate while there are enough chunks to overlap the two directions
+    size_t widest = src_row[0] > dst_row[0] ? src_row[0] : dst_row[0];
+    long chunk = (long)((16u << 20) / widest);
+    if (chunk < 1) chunk = 1;
+    const bool pipelined = (h2d || d2h) && pl->batch > 2 * chunk;
+    if (!pipelined) {
+        if (h2d)
+            for (int i = 0; i < 2; i++)
+                if (src[i] >= 0) CK(cudaMemcpyAsync(pl->d_buf[src[i]], pl->h_buf[src[i]], pl->bytes[src[i]], cudaMemcpyHostToDevice, pl->stream));
+        int rc = launch_rows(pl, direction, pl->d_buf[src[0]], src[1] >= 0 ? pl->d_buf[src[1]] : nullptr,
+                             pl->d_buf[dst[0]], dst[1] >= 0 ? pl->d_buf[dst[1]] : nullptr, pl->batch, pl->stream);
+        if (rc) return rc;
+        if (d2h)
+            for (int i = 0; i < 2; i++)
+                if (dst[i] >= 0) CK(cudaMemcpyAsync(pl->h_buf[dst[i]], pl->d_buf[dst[i]], pl->bytes[dst[i]], cudaMemcpyDeviceToHost, pl->stream));
+    } else {
+        // order the pipeline after whatever is already queued on the plan's stream
+        CK(cudaEventRecord(pl->start_ev, pl->stream));
+        for (int i = 0; i < wfb_plan::NPIPE; i++) CK(cudaStreamWaitEvent(pl->pipe[i], pl->start_ev, 0));
+        int c = 0;
+        for (long r0 = 0; r0 < pl->batch; r0 += chunk, c++) {
+            const long rows = (pl->batch - r0 < chunk) ? pl->batch - r0 : chunk;
+            cudaStream_t s = pl->pipe[c % wfb_plan::NPIPE];
+            char *di[2] = {nullptr, nullptr}, *dout[2] = {nullptr, nullptr};
+            for (int i = 0; i < 2; i++) {
+                if (src[i] >= 0) {
+                    di[i] = (char *)pl->d_buf[src[i]] + (size_t)r0 * src_row[i];
+                    if (h2d) CK(cudaMemcpyAsync(di[i], (char *)pl->h_buf[src[i]] + (size_t)r0 * src_row[i], (size_t)rows * src_row[i], cudaMemcpyHostToDevice, s));
+                }
+                if (dst[i] >= 0) dout[i] = (char *)pl->d_buf[dst[i]] + (size_t)r0 * dst_row[i];
+            }
+            int rc = launch_rows(pl, direction, di[0], di[1], dout[0], dout[1], rows, s);
+            if (rc) return rc;
+            if (d2h)
+                for (int i = 0; i < 2; i++)
+                    if (dst[i] >= 0) CK(cudaMemcpyAsync((char *)pl->h_buf[dst[i]] + (size_t)r0 * dst_row[i], dout[i], (size_t)rows * dst_row[i], cudaMemcpyDeviceToHost, s));
+        }
+        for (int i = 0; i < wfb_plan::NPIPE; i++) {
+            CK(cudaEventRecord(pl->pipe_done[i], pl->pipe[i]));
+            CK(cudaStreamWaitEvent(pl->stream, pl->pipe_done[i], 0));
+        }
+    }
     if (flags & WFB_SYNC) CK(cudaStreamSynchronize(pl->stream));
     return WFB_OK;
 }
