@@ -42,6 +42,7 @@ struct Variant {
     int threads;       // per CTA
     int rows_per_cta;  // X
     size_t smem;       // dynamic shared memory per CTA
+    int lanes;         // batch rows per thread group: 2 for the packed-FP32 (f32x2) kernels
     std::vector<int> radices;
     launch_fn c2c, r2c, c2r;
 };
@@ -55,6 +56,7 @@ template <class PL> static std::vector<int> plan_radices() {
 
 template <typename K> static cudaError_t launch_kernel(K kernel, size_t smem, int threads, long batch, int X,
                                                        const KParams &p, cudaStream_t s) {
+    // `batch` here is the number of thread GROUPS (rows / lanes); X groups per CTA
     // the dynamic-smem attribute is per (device, function); set it once for each pair
     static std::mutex mu;
     static std::set<std::pair<int, const void *>> configured;
@@ -78,25 +80,42 @@ template <typename K> static cudaError_t launch_kernel(K kernel, size_t smem, in
 constexpr int PADQ = 16;   // one pad slot per 16 complex values: conflict-free for every plan (tools/bank_sim.py)
 
 template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers {
-    static constexpr size_t smem = sizeof(vec2<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
+    static constexpr size_t smem = sizeof(cx<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
+    static constexpr int LANES = RT<R>::LANES;
+    static long groups(long batch) { return (batch + LANES - 1) / LANES; }
     static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
         if constexpr (SPLIT_IO) {
             if (io == IO_SPLIT) {
-                if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, true, MINB>, smem, PL::T * X, batch, X, p, s);
-                return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, false, MINB>, smem, PL::T * X, batch, X, p, s);
+                if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, true, MINB>, smem, PL::T * X, groups(batch), X, p, s);
+                return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, false, MINB>, smem, PL::T * X, groups(batch), X, p, s);
             }
         }
-        if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB>, smem, PL::T * X, batch, X, p, s);
-        return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB>, smem, PL::T * X, batch, X, p, s);
+        if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB>, smem, PL::T * X, groups(batch), X, p, s);
+        return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB>, smem, PL::T * X, groups(batch), X, p, s);
     }
     static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_kernel(k_r2c<R, PL, X, PADQ, MINB>, smem, PL::T * X, batch, X, p, s);
+        return launch_kernel(k_r2c<R, PL, X, PADQ, MINB>, smem, PL::T * X, groups(batch), X, p, s);
     }
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_kernel(k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, batch, X, p, s);
+        return launch_kernel(k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, groups(batch), X, p, s);
     }
     static Variant make(const char *name) {
-        return Variant{name, PL::N, PL::T * X, X, smem, plan_radices<PL>(), &c2c, &r2c, &c2r};
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, plan_radices<PL>(), &c2c, &r2c, &c2r};
+    }
+};
+
+template <class PL, int X, int MINB> struct TileLaunchers {
+    static constexpr size_t smem = sizeof(float) * 2 * (size_t)(PL::N + 2) * X;
+    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
+        if (io == IO_SPLIT) {
+            if (dir) return launch_kernel(k_c2c_tile<float, PL, X, IO_SPLIT, true, MINB>, smem, X, batch, X, p, s);
+            return launch_kernel(k_c2c_tile<float, PL, X, IO_SPLIT, false, MINB>, smem, X, batch, X, p, s);
+        }
+        if (dir) return launch_kernel(k_c2c_tile<float, PL, X, IO_INTERLEAVED, true, MINB>, smem, X, batch, X, p, s);
+        return launch_kernel(k_c2c_tile<float, PL, X, IO_INTERLEAVED, false, MINB>, smem, X, batch, X, p, s);
+    }
+    static Variant make(const char *name) {
+        return Variant{name, PL::N, X, X, smem, 1, plan_radices<PL>(), &c2c, nullptr, nullptr};
     }
 };
 
@@ -115,6 +134,9 @@ using F32_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
 using F32_2048 = Plan<2048, 128, 0x24, 0x44, 0x44>;
 using F32_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
 using F32_8192 = Plan<8192, 512, 0x2, 0x44, 0x44, 0x44>;
+// thread-per-row plans for the tile kernels (whole transform in registers)
+using T32_32 = Plan<32, 1, 0x244>;
+using T32_64 = Plan<64, 1, 0x444>;
 // f64 core plans: radix-4 for N = 4^p, radix-2 otherwise (fft_combined.wat:727-732)
 using F64_4 = Plan<4, 1, 0x4>;
 using F64_8 = Plan<8, 1, 0x222>;
@@ -130,11 +152,18 @@ using F64_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
 using F64_8192 = Plan<8192, 512, 0x2, 0x2222, 0x2222, 0x2222>;
 
 #define V32(PL, MINB) Launchers<float, PL, XROWS(PL::T), MINB, true>::make(#PL)
+#define VTILE(PL, X, MINB) TileLaunchers<PL, X, MINB>::make(#PL "_tile")
+#define V32P(PL, MINB) Launchers<f32x2, PL, XROWS(PL::T), MINB, true>::make(#PL "_x2")
 #define V64(PL, MINB) Launchers<double, PL, XROWS(PL::T), MINB, false>::make(#PL)
 
+// Variant order = preference (variant 0 is the default).  "_x2" = packed FP32 lanes (two rows per
+// thread group, FFMA2/FADD2/FMUL2); the scalar variants stay selectable for comparison.
 static const std::vector<Variant> &variants_f32() {
     static const std::vector<Variant> v = {
+        VTILE(F32_4, 256, 2), VTILE(F32_8, 256, 2), VTILE(F32_16, 256, 2), VTILE(T32_32, 128, 2), VTILE(T32_64, 128, 1),
         V32(F32_4, 2), V32(F32_8, 2), V32(F32_16, 2), V32(F32_32, 2), V32(F32_64, 2), V32(F32_128, 2),
+        V32P(F32_256, 2), V32P(F32_512, 2), V32P(F32_1024, 2), V32P(F32_2048, 2), V32P(F32_4096, 2), V32P(F32_8192, 1),
+        V32P(F32_16, 2), V32P(F32_32, 2), V32P(F32_64, 2), V32P(F32_128, 2),
         V32(F32_256, 2), V32(F32_512, 2), V32(F32_1024, 2), V32(F32_2048, 2), V32(F32_4096, 2), V32(F32_8192, 1),
     };
     return v;
@@ -165,7 +194,7 @@ struct wfb_plan {
     std::vector<const Variant *> variants;
     int variant;
     void *d_tw_fwd[8], *d_tw_inv[8];   // per variant
-    void *d_rtw;
+    void *d_rtw[8];                    // per variant (table format depends on the lane type)
     // buffers: C2C -> plane 0 / plane 1; R2C -> time / spectrum
     void *d_buf[2];
     void *h_buf[2];
@@ -277,18 +306,28 @@ static int upload_tables(wfb_plan *pl, int vi) {
         for (int mm = 0; mm < 3; mm++) { fwd[off + 2 * (mm * l + 1)] = w[mm][0]; fwd[off + 2 * (mm * l + 1) + 1] = w[mm][1]; }
     }
     if (fwd.empty()) { fwd.assign(2, R(0)); inv.assign(2, R(0)); }
+    // packed-lane kernels read entries as (re, re, im, im)
+    auto widen = [&](std::vector<R> &t) {
+        if (v.lanes != 2) return;
+        std::vector<R> o;
+        o.reserve(t.size() * 2);
+        for (size_t i = 0; i + 1 < t.size(); i += 2) { o.push_back(t[i]); o.push_back(t[i]); o.push_back(t[i + 1]); o.push_back(t[i + 1]); }
+        t.swap(o);
+    };
+    widen(fwd); widen(inv);
     CK(cudaMalloc(&pl->d_tw_fwd[vi], fwd.size() * sizeof(R)));
     CK(cudaMalloc(&pl->d_tw_inv[vi], inv.size() * sizeof(R)));
     CK(cudaMemcpy(pl->d_tw_fwd[vi], fwd.data(), fwd.size() * sizeof(R), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pl->d_tw_inv[vi], inv.data(), inv.size() * sizeof(R), cudaMemcpyHostToDevice));
-    if (pl->kind == WFB_R2C && vi == 0) {
+    if (pl->kind == WFB_R2C) {
         // W_n^k, k = 0..M (fft_split_native_f32.wat:1167-1191; fft_real_combined.wat:931-948)
         int rf = sizeof(R) == 8 ? ((pl->n == 8 || pl->n == 32) ? TW_EXACT : TW_F64) : TW_F32_SPLIT;
         std::vector<R> rre, rim, packed;
         base_twiddles<R>(rf, pl->n, m + 1, rre, rim);
         for (int k = 0; k <= m; k++) { packed.push_back(rre[k]); packed.push_back(rim[k]); }
-        CK(cudaMalloc(&pl->d_rtw, packed.size() * sizeof(R)));
-        CK(cudaMemcpy(pl->d_rtw, packed.data(), packed.size() * sizeof(R), cudaMemcpyHostToDevice));
+        widen(packed);
+        CK(cudaMalloc(&pl->d_rtw[vi], packed.size() * sizeof(R)));
+        CK(cudaMemcpy(pl->d_rtw[vi], packed.data(), packed.size() * sizeof(R), cudaMemcpyHostToDevice));
     }
     return WFB_OK;
 }
@@ -355,7 +394,8 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
     pl->variant = 0;
     const std::vector<Variant> &all = precision == WFB_F64 ? variants_f64() : variants_f32();
     for (const Variant &v : all)
-        if (v.core_n == pl->core_n && pl->variants.size() < 8) pl->variants.push_back(&v);
+        if (v.core_n == pl->core_n && pl->variants.size() < 8 && (kind == WFB_C2C ? v.c2c != nullptr : v.r2c != nullptr))
+            pl->variants.push_back(&v);
     if (pl->variants.empty()) { *err = WFB_ERR_BAD_SIZE; delete pl; return nullptr; }
     *err = plan_init(pl);
     if (*err) { wfb_plan_destroy(pl); return nullptr; }
@@ -376,7 +416,7 @@ void wfb_plan_destroy(wfb_plan *pl) {
     }
     if (pl->start_ev) cudaEventDestroy(pl->start_ev);
     for (int i = 0; i < 8; i++) { if (pl->d_tw_fwd[i]) cudaFree(pl->d_tw_fwd[i]); if (pl->d_tw_inv[i]) cudaFree(pl->d_tw_inv[i]); }
-    if (pl->d_rtw) cudaFree(pl->d_rtw);
+    for (int i = 0; i < 8; i++) if (pl->d_rtw[i]) cudaFree(pl->d_rtw[i]);
     for (int i = 0; i < 2; i++) if (pl->d_buf[i]) cudaFree(pl->d_buf[i]);
     if (pl->host_alias) { if (pl->h_buf[1]) cudaFreeHost(pl->h_buf[1]); }
     else for (int i = 0; i < 2; i++) if (pl->h_buf[i]) cudaFreeHost(pl->h_buf[i]);
@@ -416,7 +456,7 @@ static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void 
     KParams p;
     p.in0 = in0; p.in1 = in1; p.out0 = out0; p.out1 = out1;
     p.tw = direction == WFB_INVERSE ? pl->d_tw_inv[pl->variant] : pl->d_tw_fwd[pl->variant];
-    p.rtw = pl->d_rtw;
+    p.rtw = pl->d_rtw[pl->variant];
     p.batch = rows;
     p.scale = 1.0 / (double)pl->n;
     cudaError_t e;

@@ -81,33 +81,82 @@ struct Plan {
 };
 
 // ----------------------------------------------------------------------------------------
-// small vector helpers
+// arithmetic types.  Three "real" types run through the same engine:
+//   float   one f32 transform per thread group
+//   double  one f64 transform per thread group
+//   f32x2   TWO f32 transforms (adjacent batch rows) in the two lanes of Blackwell's packed-FP32
+//           instructions (FADD2 / FMUL2 / FFMA2, sm_100+): one issue slot does the work of two.
+//           The engine is issue-bound, not FP32-pipe-bound (ncu: fma pipe 30 %, issue 70 %), so
+//           halving the instruction count per transform is what moves it toward the HBM roofline.
 // ----------------------------------------------------------------------------------------
-template <typename R> struct Vec2;
-template <> struct Vec2<float> { using type = float2; };
-template <> struct Vec2<double> { using type = double2; };
-template <typename R> using vec2 = typename Vec2<R>::type;
+struct f32x2 { float2 v; };
 
-template <typename R> __device__ __forceinline__ vec2<R> mk2(R a, R b) { vec2<R> v; v.x = a; v.y = b; return v; }
-template <typename R> __device__ __forceinline__ vec2<R> cmul(vec2<R> w, vec2<R> v) {
-    // (wr*vr - wi*vi, wr*vi + wi*vr): fft_split_native_f32.wat:826-837 / fft_combined.wat:417-419
-    return mk2<R>(w.x * v.x - w.y * v.y, w.x * v.y + w.y * v.x);
+__device__ __forceinline__ float radd(float a, float b) { return a + b; }
+__device__ __forceinline__ float rsub(float a, float b) { return a - b; }
+__device__ __forceinline__ float rmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float rfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float rneg(float a) { return -a; }
+__device__ __forceinline__ double radd(double a, double b) { return a + b; }
+__device__ __forceinline__ double rsub(double a, double b) { return a - b; }
+__device__ __forceinline__ double rmul(double a, double b) { return a * b; }
+__device__ __forceinline__ double rfma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ double rneg(double a) { return -a; }
+__device__ __forceinline__ f32x2 radd(f32x2 a, f32x2 b) { return {__fadd2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f32x2 rsub(f32x2 a, f32x2 b) { return {__ffma2_rn(b.v, make_float2(-1.f, -1.f), a.v)}; }
+__device__ __forceinline__ f32x2 rmul(f32x2 a, f32x2 b) { return {__fmul2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f32x2 rfma(f32x2 a, f32x2 b, f32x2 c) { return {__ffma2_rn(a.v, b.v, c.v)}; }
+__device__ __forceinline__ f32x2 rneg(f32x2 a) { return {__fmul2_rn(a.v, make_float2(-1.f, -1.f))}; }
+
+template <typename R> struct RT;
+template <> struct RT<float> {
+    using scalar = float; using twel = float2;
+    static constexpr int LANES = 1;
+    static __device__ __forceinline__ float splat(float s) { return s; }
+};
+template <> struct RT<double> {
+    using scalar = double; using twel = double2;
+    static constexpr int LANES = 1;
+    static __device__ __forceinline__ double splat(double s) { return s; }
+};
+template <> struct RT<f32x2> {
+    using scalar = float; using twel = float4;      // table entry (re, re, im, im)
+    static constexpr int LANES = 2;
+    static __device__ __forceinline__ f32x2 splat(float s) { return {make_float2(s, s)}; }
+};
+
+// complex value / twiddle of lane type R
+template <typename R> struct alignas(2 * sizeof(R)) cx { R x, y; };
+template <typename R> struct twd { R x, y, ny; };        // (re, im, -im)
+template <typename R> __device__ __forceinline__ cx<R> mk(R a, R b) { cx<R> v; v.x = a; v.y = b; return v; }
+template <typename R> __device__ __forceinline__ cx<R> cadd(cx<R> a, cx<R> b) { return mk<R>(radd(a.x, b.x), radd(a.y, b.y)); }
+template <typename R> __device__ __forceinline__ cx<R> csub(cx<R> a, cx<R> b) { return mk<R>(rsub(a.x, b.x), rsub(a.y, b.y)); }
+// (wr*vr - wi*vi, wr*vi + wi*vr): the reference's product (fft_split_native_f32.wat:826-837,
+// fft_combined.wat:417-419) with the second term of each component fused (FMA)
+template <typename R> __device__ __forceinline__ cx<R> cmul(twd<R> w, cx<R> v) {
+    return mk<R>(rfma(w.ny, v.y, rmul(w.x, v.x)), rfma(w.y, v.x, rmul(w.x, v.y)));
 }
-template <typename R> __device__ __forceinline__ vec2<R> cadd(vec2<R> a, vec2<R> b) { return mk2<R>(a.x + b.x, a.y + b.y); }
-template <typename R> __device__ __forceinline__ vec2<R> csub(vec2<R> a, vec2<R> b) { return mk2<R>(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ twd<float> ld_tw(const float2 *p) { float2 t = __ldg(p); return {t.x, t.y, -t.y}; }
+__device__ __forceinline__ twd<double> ld_tw(const double2 *p) { double2 t = __ldg(p); return {t.x, t.y, -t.y}; }
+__device__ __forceinline__ twd<f32x2> ld_tw(const float4 *p) {
+    float4 t = __ldg(p);
+    f32x2 re = {make_float2(t.x, t.y)}, im = {make_float2(t.z, t.w)};
+    return {re, im, rneg(im)};
+}
 
 // shared-memory slot of logical element p (units of one complex value).  One pad slot per PADQ
 // elements keeps both the contiguous writes (tid + e*T) and the strided gathers of the later
 // passes (Rp*s'*j + t' + k*s') conflict-free; verified by tools/bank_sim.py for every plan.
-template <int PADQ> __device__ __forceinline__ constexpr int pad_idx(int p) { return PADQ ? p + (p / PADQ) : p; }
+template <int PADQ> __host__ __device__ constexpr int pad_idx(int p) { return PADQ ? p + (p / PADQ) : p; }
 template <int PADQ> __host__ __device__ constexpr int padded_size(int n) { return PADQ ? n + (n / PADQ) : n; }
+// pad_idx(base + off) == pad_idx(base) + pad_off(off) whenever `base mod PADQ + off mod PADQ < PADQ`
+// is guaranteed by construction (see exchange()); lets every smem access use an immediate offset.
+template <int PADQ> __host__ __device__ constexpr int pad_off(int off) { return PADQ ? off + off / PADQ : off; }
 
 // mixed-radix helpers over the sub-stages of one pass
 // hi enumerates the already-transformed (more significant) digits before sub-stage q.
 __host__ __device__ constexpr int hi_count(int code, int q) { int h = 1; for (int a = 0; a < q; a++) h *= pass_radix(code, a); return h; }
 // c(hi): output-group offset contributed by those digits = sum m'_a * prod_{h<a} r_h
 __host__ __device__ constexpr int hi_to_c(int code, int q, int hi) {
-    // digits of hi: m'_0 most significant ... m'_{q-1} least significant
     int c = 0, w = hi_count(code, q);
     int mult = 1;
     for (int a = 0; a < q; a++) {
@@ -131,22 +180,30 @@ __host__ __device__ constexpr int slot_to_out(int code, int k) {
     }
     return out;
 }
+// after pass P, register slot s = i + NB*k holds logical element  tid + out_elem(s)*T
+template <class PL, int P> __host__ __device__ constexpr int out_elem(int slot) {
+    constexpr int NB = PL::E / pass_rp(PL::code(P));
+    return (slot % NB) + NB * slot_to_out(PL::code(P), slot / NB);
+}
 
 // ----------------------------------------------------------------------------------------
 // one fused pass over the E register-resident values of a thread
 // ----------------------------------------------------------------------------------------
 template <typename R, class PL, int P, bool INV>
-__device__ __forceinline__ void run_pass(vec2<R> (&x)[PL::E], const vec2<R> *__restrict__ tw, int tid) {
+__device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, int tid) {
     constexpr int CODE = PL::code(P);
     constexpr int RP = pass_rp(CODE);
     constexpr int NB = PL::E / RP;                 // register blocks per thread
     constexpr int L_IN = PL::l_in(P);
     constexpr int SP = PL::N / (L_IN * RP);        // stride on exit (s')
     constexpr int G = pass_nsub(CODE);
+    // group index of block i: j = (tid + i*T) / SP
+    constexpr bool SPLITJ = (PL::T % SP == 0);
+    const int j0 = (L_IN == 1) ? 0 : tid / SP;
     static_for<NB>([&](auto I_) {
         CIDX(i, I_);
-        const int b = tid + i * PL::T;
-        const int j = (L_IN == 1) ? 0 : b / SP;
+        const int j = (L_IN == 1) ? 0 : (SPLITJ ? j0 + i * (PL::T / SP) : (tid + i * PL::T) / SP);
+        const typename RT<R>::twel *twj = tw + j;
         static_for<G>([&](auto Q_) {
             CIDX(q, Q_);
             constexpr int r = pass_radix(CODE, q);
@@ -158,38 +215,37 @@ __device__ __forceinline__ void run_pass(vec2<R> (&x)[PL::E], const vec2<R> *__r
                 CIDX(hi, HI_);
                 constexpr int c = hi_to_c(CODE, q, hi);
                 constexpr bool unit = (L_IN == 1 && c == 0);     // group 0: W^0 = 1
-                vec2<R> w1 = mk2<R>(R(1), R(0)), w2 = w1, w3 = w1;
+                twd<R> w1, w2, w3;
                 if constexpr (!unit) {
-                    const int jq = j + L_IN * c;
-                    w1 = __ldg(tw + off + jq);
+                    w1 = ld_tw(twj + (off + L_IN * c));
                     if constexpr (r == 4) {
-                        w2 = __ldg(tw + off + lq + jq);
-                        w3 = __ldg(tw + off + 2 * lq + jq);
+                        w2 = ld_tw(twj + (off + lq + L_IN * c));
+                        w3 = ld_tw(twj + (off + 2 * lq + L_IN * c));
                     }
                 }
                 static_for<w>([&](auto LO_) {
                     CIDX(lo, LO_);
                     constexpr int k0 = hi * (w * r) + lo;
                     if constexpr (r == 2) {
-                        vec2<R> &A = x[i + NB * k0], &B = x[i + NB * (k0 + w)];
-                        const vec2<R> wb = unit ? B : cmul<R>(w1, B);
-                        const vec2<R> a = A;
+                        cx<R> &A = x[i + NB * k0], &B = x[i + NB * (k0 + w)];
+                        cx<R> wb = B;
+                        if constexpr (!unit) wb = cmul<R>(w1, B);
+                        const cx<R> a = A;
                         A = cadd<R>(a, wb);
                         B = csub<R>(a, wb);
                     } else {
-                        vec2<R> &A = x[i + NB * k0], &B = x[i + NB * (k0 + w)];
-                        vec2<R> &C = x[i + NB * (k0 + 2 * w)], &D = x[i + NB * (k0 + 3 * w)];
-                        const vec2<R> wb = unit ? B : cmul<R>(w1, B);
-                        const vec2<R> wc = unit ? C : cmul<R>(w2, C);
-                        const vec2<R> wd = unit ? D : cmul<R>(w3, D);
-                        const vec2<R> t0 = cadd<R>(A, wc), t1 = csub<R>(A, wc);
-                        const vec2<R> t2 = cadd<R>(wb, wd), t3 = csub<R>(wb, wd);
+                        cx<R> &A = x[i + NB * k0], &B = x[i + NB * (k0 + w)];
+                        cx<R> &C = x[i + NB * (k0 + 2 * w)], &D = x[i + NB * (k0 + 3 * w)];
+                        cx<R> wb = B, wc = C, wd = D;
+                        if constexpr (!unit) { wb = cmul<R>(w1, B); wc = cmul<R>(w2, C); wd = cmul<R>(w3, D); }
+                        const cx<R> t0 = cadd<R>(A, wc), t1 = csub<R>(A, wc);
+                        const cx<R> t2 = cadd<R>(wb, wd), t3 = csub<R>(wb, wd);
                         A = cadd<R>(t0, t2);
                         C = csub<R>(t0, t2);
                         // forward: out1 = t1 - i*t3, out3 = t1 + i*t3; the inverse swaps them
                         // (fft_split_native_f32.wat:785-788)
-                        const vec2<R> m1 = mk2<R>(t1.x + t3.y, t1.y - t3.x);
-                        const vec2<R> m3 = mk2<R>(t1.x - t3.y, t1.y + t3.x);
+                        const cx<R> m1 = mk<R>(radd(t1.x, t3.y), rsub(t1.y, t3.x));
+                        const cx<R> m3 = mk<R>(rsub(t1.x, t3.y), radd(t1.y, t3.x));
                         B = INV ? m3 : m1;
                         D = INV ? m1 : m3;
                     }
@@ -199,13 +255,8 @@ __device__ __forceinline__ void run_pass(vec2<R> (&x)[PL::E], const vec2<R> *__r
     });
 }
 
-// after a pass, register slot (i, k) holds logical element  tid + (i + NB*k')*T,  k' = slot_to_out(k)
-template <class PL, int P> __host__ __device__ constexpr int out_elem(int i, int k) {
-    return i + (PL::E / pass_rp(PL::code(P))) * slot_to_out(PL::code(P), k);
-}
-
 // ----------------------------------------------------------------------------------------
-// barriers scoped to the threads of one transform
+// barriers scoped to the threads of one transform (pair)
 // ----------------------------------------------------------------------------------------
 template <int T, int X> __device__ __forceinline__ void sync_transform(int xi) {
     if constexpr (T <= 32) {
@@ -217,43 +268,50 @@ template <int T, int X> __device__ __forceinline__ void sync_transform(int xi) {
     }
 }
 
-// exchange: registers -> smem (layout of pass P's outputs) -> registers (layout of pass P+1's inputs)
-template <typename R, class PL, int P, int PADQ, int X>
-__device__ __forceinline__ void exchange(vec2<R> (&x)[PL::E], vec2<R> *sm, int tid, int xi, bool need_pre_sync) {
-    constexpr int CODE = PL::code(P);
-    constexpr int RP = pass_rp(CODE);
-    constexpr int NB = PL::E / RP;
-    if (need_pre_sync) sync_transform<PL::T, X>(xi);   // everyone finished reading the previous contents
+// registers -> smem in the natural layout of pass P's outputs (element tid + e*T at pad(tid)+pad_off(e*T))
+template <typename R, class PL, int P, int PADQ>
+__device__ __forceinline__ void spill_outputs(const cx<R> (&x)[PL::E], cx<R> *sm, int tid) {
+    static_assert(PL::T % PADQ == 0 || PADQ % PL::T == 0, "pad algebra needs T | PADQ or PADQ | T");
+    cx<R> *base = sm + pad_idx<PADQ>(tid);
     static_for<PL::E>([&](auto S_) {
         CIDX(slot, S_);
-        constexpr int i = slot % NB, k = slot / NB;
-        constexpr int e = out_elem<PL, P>(i, k);
-        sm[pad_idx<PADQ>(tid + e * PL::T)] = x[slot];
-    });
-    sync_transform<PL::T, X>(xi);
-    constexpr int CODE2 = PL::code(P + 1);
-    constexpr int RP2 = pass_rp(CODE2);
-    constexpr int NB2 = PL::E / RP2;
-    constexpr int SP2 = PL::N / (PL::l_in(P + 1) * RP2);
-    static_for<NB2>([&](auto I_) {
-        CIDX(i, I_);
-        const int b = tid + i * PL::T;
-        const int j = b / SP2, t = b % SP2;
-        const int base = RP2 * SP2 * j + t;
-        static_for<RP2>([&](auto K_) {
-            CIDX(k, K_);
-            x[i + NB2 * k] = sm[pad_idx<PADQ>(base + k * SP2)];
-        });
+        constexpr int e = out_elem<PL, P>(slot);
+        base[pad_off<PADQ>(e * PL::T)] = x[slot];
     });
 }
 
-// all passes after the first-pass inputs are in registers; leaves the last pass's outputs in x
+// smem -> registers in the gather layout of pass P's inputs
+template <typename R, class PL, int P, int PADQ>
+__device__ __forceinline__ void fill_inputs(cx<R> (&x)[PL::E], const cx<R> *sm, int tid) {
+    constexpr int RP = pass_rp(PL::code(P));
+    constexpr int NB = PL::E / RP;
+    constexpr int SP = PL::N / (PL::l_in(P) * RP);
+    constexpr bool FAST = (SP % PADQ == 0) || (PADQ % SP == 0 && (RP * SP) % PADQ == 0);
+    static_for<NB>([&](auto I_) {
+        CIDX(i, I_);
+        const int b = tid + i * PL::T;
+        const int j = b / SP, t = b % SP;
+        const int base = RP * SP * j + t;
+        if constexpr (FAST) {
+            const cx<R> *bp = sm + pad_idx<PADQ>(base);
+            static_for<RP>([&](auto K_) { CIDX(k, K_); x[i + NB * k] = bp[pad_off<PADQ>(k * SP)]; });
+        } else {
+            static_for<RP>([&](auto K_) { CIDX(k, K_); x[i + NB * k] = sm[pad_idx<PADQ>(base + k * SP)]; });
+        }
+    });
+}
+
+// all passes; on entry x holds pass 0's inputs (element tid + e*T in slot e), on exit the last
+// pass's outputs.  `smem_dirty`: other threads may still be reading smem when we get here.
 template <typename R, class PL, int PADQ, int X, bool INV, int P = 0>
-__device__ __forceinline__ void run_all(vec2<R> (&x)[PL::E], const vec2<R> *__restrict__ tw, vec2<R> *sm, int tid,
-                                        int xi, bool smem_dirty) {
+__device__ __forceinline__ void run_all(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, cx<R> *sm,
+                                        int tid, int xi, bool smem_dirty) {
     run_pass<R, PL, P, INV>(x, tw, tid);
     if constexpr (P + 1 < PL::npass()) {
-        exchange<R, PL, P, PADQ, X>(x, sm, tid, xi, smem_dirty || P > 0);
+        if (smem_dirty || P > 0) sync_transform<PL::T, X>(xi);
+        spill_outputs<R, PL, P, PADQ>(x, sm, tid);
+        sync_transform<PL::T, X>(xi);
+        fill_inputs<R, PL, P + 1, PADQ>(x, sm, tid);
         run_all<R, PL, PADQ, X, INV, P + 1>(x, tw, sm, tid, xi, true);
     }
 }
@@ -264,8 +322,8 @@ __device__ __forceinline__ void run_all(vec2<R> (&x)[PL::E], const vec2<R> *__re
 struct KParams {
     const void *in0, *in1;     // input planes
     void *out0, *out1;         // output planes
-    const void *tw;            // stage tables for this direction (complex entries)
-    const void *rtw;           // W_Nreal^k, k = 0..M, for the real transforms (complex entries)
+    const void *tw;            // stage tables for this direction
+    const void *rtw;           // W_Nreal^k, k = 0..M, for the real transforms
     long batch;
     double scale;              // applied on store (1/N for the inverse c2c)
 };
@@ -276,6 +334,62 @@ enum IoMode { IO_SPLIT = 0, IO_INTERLEAVED = 1 };
 template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void st_stream(V *p, V v) { __stcs(p, v); }
 
+// Global <-> register movement of one complex element for each lane type.  `rs` is the row stride
+// in elements of the pointed-to type; lane 1 of f32x2 is the NEXT batch row (clamped onto lane 0's
+// row when the batch is odd and this is the last group: loaded twice, stored once).
+template <typename R> struct GIO;
+template <> struct GIO<float> {
+    static __device__ __forceinline__ cx<float> ld_split(const float *re, const float *im, long, bool) { return mk<float>(ld_stream(re), ld_stream(im)); }
+    static __device__ __forceinline__ cx<float> ld_il(const float2 *z, long, bool) { float2 v = ld_stream(z); return mk<float>(v.x, v.y); }
+    static __device__ __forceinline__ void st_split(float *re, float *im, long, bool, cx<float> v) { st_stream(re, v.x); st_stream(im, v.y); }
+    static __device__ __forceinline__ void st_il(float2 *z, long, bool, cx<float> v) { st_stream(z, make_float2(v.x, v.y)); }
+    static __device__ __forceinline__ float re0(cx<float> v) { return v.x; }
+};
+template <> struct GIO<double> {
+    static __device__ __forceinline__ cx<double> ld_split(const double *re, const double *im, long, bool) { return mk<double>(ld_stream(re), ld_stream(im)); }
+    static __device__ __forceinline__ cx<double> ld_il(const double2 *z, long, bool) { double2 v = ld_stream(z); return mk<double>(v.x, v.y); }
+    static __device__ __forceinline__ void st_split(double *re, double *im, long, bool, cx<double> v) { st_stream(re, v.x); st_stream(im, v.y); }
+    static __device__ __forceinline__ void st_il(double2 *z, long, bool, cx<double> v) { st_stream(z, make_double2(v.x, v.y)); }
+};
+template <> struct GIO<f32x2> {
+    static __device__ __forceinline__ cx<f32x2> ld_split(const float *re, const float *im, long rs, bool) {
+        f32x2 a = {make_float2(ld_stream(re), ld_stream(re + rs))};
+        f32x2 b = {make_float2(ld_stream(im), ld_stream(im + rs))};
+        return mk<f32x2>(a, b);
+    }
+    static __device__ __forceinline__ cx<f32x2> ld_il(const float2 *z, long rs, bool) {
+        float2 a = ld_stream(z), b = ld_stream(z + rs);
+        return mk<f32x2>({make_float2(a.x, b.x)}, {make_float2(a.y, b.y)});
+    }
+    static __device__ __forceinline__ void st_split(float *re, float *im, long rs, bool two, cx<f32x2> v) {
+        st_stream(re, v.x.v.x); st_stream(im, v.y.v.x);
+        if (two) { st_stream(re + rs, v.x.v.y); st_stream(im + rs, v.y.v.y); }
+    }
+    static __device__ __forceinline__ void st_il(float2 *z, long rs, bool two, cx<f32x2> v) {
+        st_stream(z, make_float2(v.x.v.x, v.y.v.x));
+        if (two) st_stream(z + rs, make_float2(v.x.v.y, v.y.v.y));
+    }
+};
+template <typename R> struct VecOf;
+template <> struct VecOf<float> { using s = float; using v2 = float2; };
+template <> struct VecOf<double> { using s = double; using v2 = double2; };
+template <> struct VecOf<f32x2> { using s = float; using v2 = float2; };
+
+// per-thread-group row bookkeeping
+template <typename R, int T, int X> struct Rows {
+    int xi, tid;
+    long row;          // first row of this group
+    bool active, two;  // any row valid / second lane's row valid
+    long lane1;        // element offset multiplier of lane 1's row (0 when clamped)
+    __device__ __forceinline__ Rows(long batch) {
+        xi = threadIdx.x / T; tid = threadIdx.x % T;
+        row = ((long)blockIdx.x * X + xi) * RT<R>::LANES;
+        active = row < batch;
+        two = RT<R>::LANES == 2 && row + 1 < batch;
+        lane1 = two ? 1 : 0;
+    }
+};
+
 // ----------------------------------------------------------------------------------------
 // Transform 1 and 3 (f32) / 4 (f64): batched c2c, split or interleaved I/O
 // ----------------------------------------------------------------------------------------
@@ -283,59 +397,51 @@ template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c(KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using S = typename VecOf<R>::s;
+    using V2 = typename VecOf<R>::v2;
     constexpr int LAST = PL::npass() - 1;
-    const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
-    const long row = (long)blockIdx.x * X + xi;
-    const bool active = row < p.batch;
-    vec2<R> *sm = reinterpret_cast<vec2<R> *>(smem_raw) + (size_t)xi * padded_size<PADQ>(PL::N);
-    const vec2<R> *tw = reinterpret_cast<const vec2<R> *>(p.tw);
-    vec2<R> x[PL::E];
+    const Rows<R, PL::T, X> g(p.batch);
+    const int tid = g.tid;
+    cx<R> *sm = reinterpret_cast<cx<R> *>(smem_raw) + (size_t)g.xi * padded_size<PADQ>(PL::N);
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+    cx<R> x[PL::E];
+    const long rs = g.lane1 * PL::N;
 
-    if (active) {
+    if (g.active) {
         if constexpr (IO == IO_SPLIT) {
-            const R *re = reinterpret_cast<const R *>(p.in0) + row * PL::N;
-            const R *im = reinterpret_cast<const R *>(p.in1) + row * PL::N;
-#pragma unroll
-            for (int e = 0; e < PL::E; e++) x[e].x = ld_stream(re + tid + e * PL::T);
-#pragma unroll
-            for (int e = 0; e < PL::E; e++) x[e].y = ld_stream(im + tid + e * PL::T);
+            const S *re = reinterpret_cast<const S *>(p.in0) + g.row * PL::N + tid;
+            const S *im = reinterpret_cast<const S *>(p.in1) + g.row * PL::N + tid;
+            static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = GIO<R>::ld_split(re + e * PL::T, im + e * PL::T, rs, g.two); });
         } else {
-            const vec2<R> *z = reinterpret_cast<const vec2<R> *>(p.in0) + row * PL::N;
-#pragma unroll
-            for (int e = 0; e < PL::E; e++) x[e] = ld_stream(z + tid + e * PL::T);
+            const V2 *z = reinterpret_cast<const V2 *>(p.in0) + g.row * PL::N + tid;
+            static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = GIO<R>::ld_il(z + e * PL::T, rs, g.two); });
         }
     } else {
-#pragma unroll
-        for (int e = 0; e < PL::E; e++) x[e] = mk2<R>(R(0), R(0));
+        static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = mk<R>(RT<R>::splat(0), RT<R>::splat(0)); });
     }
 
-    run_all<R, PL, PADQ, X, INV>(x, tw, sm, tid, xi, false);
+    run_all<R, PL, PADQ, X, INV>(x, tw, sm, tid, g.xi, false);
 
-    if (active) {
-        constexpr int RP = pass_rp(PL::code(LAST));
-        constexpr int NB = PL::E / RP;
-        const R sc = (R)p.scale;
+    if (g.active) {
+        const R sc = RT<R>::splat((S)p.scale);
         if constexpr (IO == IO_SPLIT) {
-            R *re = reinterpret_cast<R *>(p.out0) + row * PL::N;
-            R *im = reinterpret_cast<R *>(p.out1) + row * PL::N;
+            S *re = reinterpret_cast<S *>(p.out0) + g.row * PL::N + tid;
+            S *im = reinterpret_cast<S *>(p.out1) + g.row * PL::N + tid;
             static_for<PL::E>([&](auto S_) {
                 CIDX(slot, S_);
-                constexpr int e = out_elem<PL, LAST>(slot % NB, slot / NB);
-                st_stream(re + tid + e * PL::T, INV ? x[slot].x * sc : x[slot].x);
-            });
-            static_for<PL::E>([&](auto S_) {
-                CIDX(slot, S_);
-                constexpr int e = out_elem<PL, LAST>(slot % NB, slot / NB);
-                st_stream(im + tid + e * PL::T, INV ? x[slot].y * sc : x[slot].y);
+                constexpr int e = out_elem<PL, LAST>(slot);
+                cx<R> v = x[slot];
+                if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                GIO<R>::st_split(re + e * PL::T, im + e * PL::T, rs, g.two, v);
             });
         } else {
-            vec2<R> *z = reinterpret_cast<vec2<R> *>(p.out0) + row * PL::N;
+            V2 *z = reinterpret_cast<V2 *>(p.out0) + g.row * PL::N + tid;
             static_for<PL::E>([&](auto S_) {
                 CIDX(slot, S_);
-                constexpr int e = out_elem<PL, LAST>(slot % NB, slot / NB);
-                vec2<R> v = x[slot];
-                if (INV) v = mk2<R>(v.x * sc, v.y * sc);
-                st_stream(z + tid + e * PL::T, v);
+                constexpr int e = out_elem<PL, LAST>(slot);
+                cx<R> v = x[slot];
+                if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                GIO<R>::st_il(z + e * PL::T, rs, g.two, v);
             });
         }
     }
@@ -348,42 +454,41 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c(KParams p) {
 // memory straight into the coalesced spectrum store (cf. $rfft_postprocess_split :1471-1559,
 // fft_real_combined.wat:455-592).
 // ----------------------------------------------------------------------------------------
-template <typename R> struct RealPost;
-
-// f32 flavour: one twiddle W^k serves both X[k] and X[M-k]
-template <> struct RealPost<float> {
-    __device__ static __forceinline__ void pair(float2 z, float2 zm, float2 w, float2 wm, float2 &xk, float2 &xm) {
-        (void)wm;
-        float gr = z.x + zm.x, gi = z.y - zm.y, hr = z.y + zm.y, hi = zm.x - z.x;
-        float tr = w.x * hr - w.y * hi, ti = w.x * hi + w.y * hr;
-        xk = make_float2(0.5f * (gr + tr), 0.5f * (gi + ti));
-        xm = make_float2(0.5f * (gr - tr), 0.5f * (ti - gi));
+template <typename R> struct RealPost {
+    // f32 flavour (float and f32x2): one twiddle W^k serves both X[k] and X[M-k]
+    static __device__ __forceinline__ void pair(cx<R> z, cx<R> zm, twd<R> w, twd<R>, cx<R> &xk, cx<R> &xm) {
+        const R half = RT<R>::splat(0.5f);
+        const R gr = radd(z.x, zm.x), gi = rsub(z.y, zm.y), hr = radd(z.y, zm.y), hi = rsub(zm.x, z.x);
+        const R tr = rfma(w.ny, hi, rmul(w.x, hr)), ti = rfma(w.y, hr, rmul(w.x, hi));
+        xk = mk<R>(rmul(half, radd(gr, tr)), rmul(half, radd(gi, ti)));
+        xm = mk<R>(rmul(half, rsub(gr, tr)), rmul(half, rsub(ti, gi)));
     }
     // X[M/2]: the reference's last vector iteration stores the mirrored form last (:1527-1545);
     // the M = 32 fused ending stores conj(Z[M/2]) (:2710)
-    __device__ static __forceinline__ float2 middle(float2 z, float2 w, int m) {
-        if (m == 32) return make_float2(z.x, -z.y);
-        float2 a, b;
+    static __device__ __forceinline__ cx<R> middle(cx<R> z, twd<R> w, int m) {
+        if (m == 32) return mk<R>(z.x, rneg(z.y));
+        cx<R> a, b;
         pair(z, z, w, w, a, b);
         return b;
     }
 };
 // f64 flavour: T[k] and T[M-k] are separately tabulated (fft_real_combined.wat:502-503,533-534)
 template <> struct RealPost<double> {
-    __device__ static __forceinline__ double2 one(double2 z, double2 zm, double2 w) {
+    using C = cx<double>;
+    static __device__ __forceinline__ C one(C z, C zm, twd<double> w) {
         double sr = z.x + zm.x, si = z.y - zm.y, dr = z.x - zm.x, di = z.y + zm.y;
         double wdr = w.y * dr + w.x * di, wdi = w.y * di - w.x * dr;
-        return make_double2(0.5 * (sr + wdr), 0.5 * (si + wdi));
+        return mk<double>(0.5 * (sr + wdr), 0.5 * (si + wdi));
     }
-    __device__ static __forceinline__ void pair(double2 z, double2 zm, double2 w, double2 wm, double2 &xk, double2 &xm) {
+    static __device__ __forceinline__ void pair(C z, C zm, twd<double> w, twd<double> wm, C &xk, C &xm) {
         xk = one(z, zm, w);
         xm = one(zm, z, wm);
     }
-    __device__ static __forceinline__ double2 middle(double2 z, double2 w, int) {
+    static __device__ __forceinline__ C middle(C z, twd<double> w, int) {
         // sum = (2 re, 0), diff = (0, 2 im)  (fft_real_combined.wat:1031-1050)
         double sr = 2.0 * z.x, si = 0.0, dr = 0.0, di = 2.0 * z.y;
         double wdr = w.y * dr + w.x * di, wdi = w.y * di - w.x * dr;
-        return make_double2(0.5 * (sr + wdr), 0.5 * (si + wdi));
+        return mk<double>(0.5 * (sr + wdr), 0.5 * (si + wdi));
     }
 };
 
@@ -391,63 +496,56 @@ template <typename R, class PL, int X, int PADQ, int MINB>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using V2 = typename VecOf<R>::v2;
     constexpr int M = PL::N;
     constexpr int LAST = PL::npass() - 1;
-    const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
-    const long row = (long)blockIdx.x * X + xi;
-    const bool active = row < p.batch;
-    vec2<R> *sm = reinterpret_cast<vec2<R> *>(smem_raw) + (size_t)xi * padded_size<PADQ>(M);
-    const vec2<R> *tw = reinterpret_cast<const vec2<R> *>(p.tw);
-    const vec2<R> *rtw = reinterpret_cast<const vec2<R> *>(p.rtw);
-    vec2<R> x[PL::E];
+    const Rows<R, PL::T, X> g(p.batch);
+    const int tid = g.tid;
+    cx<R> *sm = reinterpret_cast<cx<R> *>(smem_raw) + (size_t)g.xi * padded_size<PADQ>(M);
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+    const typename RT<R>::twel *rtw = reinterpret_cast<const typename RT<R>::twel *>(p.rtw);
+    cx<R> x[PL::E];
 
-    if (active) {
-        const vec2<R> *z = reinterpret_cast<const vec2<R> *>(p.in0) + row * M;   // z[j] = x[2j] + i x[2j+1]
-#pragma unroll
-        for (int e = 0; e < PL::E; e++) x[e] = ld_stream(z + tid + e * PL::T);
+    if (g.active) {
+        const V2 *z = reinterpret_cast<const V2 *>(p.in0) + g.row * M + tid;   // z[j] = x[2j] + i x[2j+1]
+        static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = GIO<R>::ld_il(z + e * PL::T, g.lane1 * M, g.two); });
     } else {
-#pragma unroll
-        for (int e = 0; e < PL::E; e++) x[e] = mk2<R>(R(0), R(0));
+        static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = mk<R>(RT<R>::splat(0), RT<R>::splat(0)); });
     }
 
-    run_all<R, PL, PADQ, X, false>(x, tw, sm, tid, xi, false);
+    run_all<R, PL, PADQ, X, false>(x, tw, sm, tid, g.xi, false);
 
     // Z -> shared memory in natural order
-    {
-        constexpr int RP = pass_rp(PL::code(LAST));
-        constexpr int NB = PL::E / RP;
-        if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
-        static_for<PL::E>([&](auto S_) {
-            CIDX(slot, S_);
-            constexpr int e = out_elem<PL, LAST>(slot % NB, slot / NB);
-            sm[pad_idx<PADQ>(tid + e * PL::T)] = x[slot];
-        });
-        sync_transform<PL::T, X>(xi);
-    }
-    if (!active) return;
+    if (PL::npass() > 1) sync_transform<PL::T, X>(g.xi);
+    spill_outputs<R, PL, LAST, PADQ>(x, sm, tid);
+    sync_transform<PL::T, X>(g.xi);
+    if (!g.active) return;
 
-    vec2<R> *out = reinterpret_cast<vec2<R> *>(p.out0) + row * (M + 1);
+    V2 *out = reinterpret_cast<V2 *>(p.out0) + g.row * (M + 1);
+    const long rs = g.lane1 * (M + 1);
     // pairs (k, M-k), k = tid + i*T over 0 .. M/2-1; k = 0 is DC/Nyquist; thread 0 adds k = M/2
     constexpr int HALF = M / 2;
     constexpr int PER = (HALF + PL::T - 1) / PL::T;
-#pragma unroll
-    for (int i = 0; i < PER; i++) {
+    const R zero = RT<R>::splat(0);
+    static_for<PER>([&](auto I_) {
+        CIDX(i, I_);
         const int k = tid + i * PL::T;
-        if (k >= HALF) break;
-        if (k == 0) {
-            vec2<R> z0 = sm[0];
-            st_stream(out, mk2<R>(z0.x + z0.y, R(0)));
-            st_stream(out + M, mk2<R>(z0.x - z0.y, R(0)));
-            vec2<R> zh = sm[pad_idx<PADQ>(HALF)];
-            st_stream(out + HALF, RealPost<R>::middle(zh, __ldg(rtw + HALF), M));
-        } else {
-            vec2<R> z = sm[pad_idx<PADQ>(k)], zm = sm[pad_idx<PADQ>(M - k)];
-            vec2<R> xk, xm;
-            RealPost<R>::pair(z, zm, __ldg(rtw + k), __ldg(rtw + (M - k)), xk, xm);
-            st_stream(out + k, xk);
-            st_stream(out + (M - k), xm);
+        if (k < HALF) {
+            if (i == 0 && k == 0) {
+                const cx<R> z0 = sm[0];
+                GIO<R>::st_il(out, rs, g.two, mk<R>(radd(z0.x, z0.y), zero));
+                GIO<R>::st_il(out + M, rs, g.two, mk<R>(rsub(z0.x, z0.y), zero));
+                const cx<R> zh = sm[pad_idx<PADQ>(HALF)];
+                GIO<R>::st_il(out + HALF, rs, g.two, RealPost<R>::middle(zh, ld_tw(rtw + HALF), M));
+            } else {
+                const cx<R> z = sm[pad_idx<PADQ>(k)], zm = sm[pad_idx<PADQ>(M - k)];
+                cx<R> xk, xm;
+                RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);
+                GIO<R>::st_il(out + k, rs, g.two, xk);
+                GIO<R>::st_il(out + (M - k), rs, g.two, xm);
+            }
         }
-    }
+    });
 }
 
 // ----------------------------------------------------------------------------------------
@@ -460,54 +558,160 @@ template <typename R, class PL, int X, int PADQ, int MINB>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_c2r(KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using S = typename VecOf<R>::s;
+    using V2 = typename VecOf<R>::v2;
     constexpr int M = PL::N;
     constexpr int LAST = PL::npass() - 1;
-    const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
-    const long row = (long)blockIdx.x * X + xi;
-    const bool active = row < p.batch;
-    vec2<R> *sm = reinterpret_cast<vec2<R> *>(smem_raw) + (size_t)xi * padded_size<PADQ>(M);
-    const vec2<R> *tw = reinterpret_cast<const vec2<R> *>(p.tw);
-    const vec2<R> *rtw = reinterpret_cast<const vec2<R> *>(p.rtw);
-    vec2<R> x[PL::E];
+    const Rows<R, PL::T, X> g(p.batch);
+    const int tid = g.tid;
+    cx<R> *sm = reinterpret_cast<cx<R> *>(smem_raw) + (size_t)g.xi * padded_size<PADQ>(M);
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+    const typename RT<R>::twel *rtw = reinterpret_cast<const typename RT<R>::twel *>(p.rtw);
+    cx<R> x[PL::E];
 
     constexpr int HALF = M / 2;
     constexpr int PER = (HALF + PL::T - 1) / PL::T;
-    const R sc = R(0.5) / R(M);
-    if (active) {
-        const vec2<R> *in = reinterpret_cast<const vec2<R> *>(p.in0) + row * (M + 1);
-#pragma unroll
-        for (int i = 0; i < PER; i++) {
+    const R sc = RT<R>::splat(S(0.5) / S(M));
+    if (g.active) {
+        const V2 *in = reinterpret_cast<const V2 *>(p.in0) + g.row * (M + 1);
+        const long rs = g.lane1 * (M + 1);
+        static_for<PER>([&](auto I_) {
+            CIDX(i, I_);
             const int k = tid + i * PL::T;
-            if (k >= HALF) break;
-            if (k == 0) {
-                const R x0 = ld_stream(in).x, xm = ld_stream(in + M).x;      // real parts only (:1679-1684)
-                sm[0] = mk2<R>((x0 + xm) * sc, (x0 - xm) * sc);
+            if (k < HALF) {
+                if (i == 0 && k == 0) {
+                    // real parts only (:1679-1684)
+                    const cx<R> a0 = GIO<R>::ld_il(in, rs, g.two), am = GIO<R>::ld_il(in + M, rs, g.two);
+                    sm[0] = mk<R>(rmul(radd(a0.x, am.x), sc), rmul(rsub(a0.x, am.x), sc));
+                }
+                const int kk = (k == 0) ? HALF : k;     // thread 0's slot k = 0 also covers the self-paired k = M/2
+                const cx<R> a = GIO<R>::ld_il(in + kk, rs, g.two), b = GIO<R>::ld_il(in + (M - kk), rs, g.two);
+                const twd<R> w = ld_tw(rtw + kk);
+                const R gr = radd(a.x, b.x), gi = rsub(a.y, b.y), ur = rsub(a.x, b.x), ui = radd(a.y, b.y);
+                // hr = wr*ur + wi*ui, hi = wr*ui - wi*ur   (conj(W) * u)
+                const R hr = rfma(w.y, ui, rmul(w.x, ur)), hi = rfma(w.ny, ur, rmul(w.x, ui));
+                // forward store first, mirrored second: at k = M/2 the mirrored form survives (:1722-1740)
+                sm[pad_idx<PADQ>(kk)] = mk<R>(rmul(sc, rsub(gr, hi)), rmul(sc, radd(gi, hr)));
+                sm[pad_idx<PADQ>(M - kk)] = mk<R>(rmul(sc, radd(gr, hi)), rmul(sc, rsub(hr, gi)));
             }
-            const int kk = (k == 0) ? HALF : k;     // thread 0's slot k = 0 also covers the self-paired k = M/2
-            const vec2<R> a = ld_stream(in + kk), b = ld_stream(in + (M - kk));
-            const vec2<R> w = __ldg(rtw + kk);
-            const R gr = a.x + b.x, gi = a.y - b.y, ur = a.x - b.x, ui = a.y + b.y;
-            const R hr = w.x * ur + w.y * ui, hi = w.x * ui - w.y * ur;
-            // forward store first, mirrored second: at k = M/2 the mirrored form survives (:1722-1740)
-            sm[pad_idx<PADQ>(kk)] = mk2<R>(sc * (gr - hi), sc * (gi + hr));
-            sm[pad_idx<PADQ>(M - kk)] = mk2<R>(sc * (gr + hi), sc * (hr - gi));
-        }
+        });
     }
-    sync_transform<PL::T, X>(xi);
-#pragma unroll
-    for (int e = 0; e < PL::E; e++) x[e] = sm[pad_idx<PADQ>(tid + e * PL::T)];
+    sync_transform<PL::T, X>(g.xi);
+    {
+        const cx<R> *base = sm + pad_idx<PADQ>(tid);
+        static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = base[pad_off<PADQ>(e * PL::T)]; });
+    }
 
-    run_all<R, PL, PADQ, X, true>(x, tw, sm, tid, xi, true);
+    run_all<R, PL, PADQ, X, true>(x, tw, sm, tid, g.xi, true);
 
-    if (active) {
-        constexpr int RP = pass_rp(PL::code(LAST));
-        constexpr int NB = PL::E / RP;
-        vec2<R> *z = reinterpret_cast<vec2<R> *>(p.out0) + row * M;
+    if (g.active) {
+        V2 *z = reinterpret_cast<V2 *>(p.out0) + g.row * M + tid;
         static_for<PL::E>([&](auto S_) {
             CIDX(slot, S_);
-            constexpr int e = out_elem<PL, LAST>(slot % NB, slot / NB);
-            st_stream(z + tid + e * PL::T, x[slot]);
+            constexpr int e = out_elem<PL, LAST>(slot);
+            GIO<R>::st_il(z + e * PL::T, g.lane1 * M, g.two, x[slot]);
         });
+    }
+}
+
+
+// ----------------------------------------------------------------------------------------
+// Small-N c2c (N <= 64): one thread per transform, whole transform in registers (single pass, no
+// exchange), X rows per CTA staged through shared memory so that EVERY global access is a
+// coalesced 128-bit load/store of a dense [X][N] tile (a thread-per-row kernel reading global
+// memory directly touches 32 different 64-byte segments per instruction: ncu showed 25 % of the
+// HBM roofline at N = 16).  Row stride in smem is N + 2 complex values (N*8 + 16 bytes): the
+// per-row LDS.128/STS.128 of 8 consecutive threads then fall in 8 distinct 16-byte bank groups.
+// ----------------------------------------------------------------------------------------
+template <typename R, class PL, int X, int IO, bool INV, int MINB>
+__global__ void __launch_bounds__(X, MINB) k_c2c_tile(KParams p) {
+    static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && RT<R>::LANES == 1, "tile kernel: one thread per row");
+    static_assert(sizeof(R) == 4, "tile kernel is f32");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = PL::N;
+    constexpr int RS = N + 2;                           // row stride, complex values
+    float *smf = reinterpret_cast<float *>(smem_raw);
+    const int t = threadIdx.x;
+    const long row0 = (long)blockIdx.x * X;
+    const int rows = (p.batch - row0 < X) ? (int)(p.batch - row0) : X;
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+
+    // ---- stage in: dense tile -> padded interleaved rows
+    if constexpr (IO == IO_SPLIT) {
+        constexpr int CPR = N / 4;                      // float4 chunks per row per plane
+        const float4 *re = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.in0) + row0 * N);
+        const float4 *im = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.in1) + row0 * N);
+#pragma unroll
+        for (int f = t; f < X * CPR; f += X) {
+            const int r = f / CPR, c = f % CPR;
+            if (r < rows) {
+                const float4 a = ld_stream(re + f), b = ld_stream(im + f);
+                float4 *dst = reinterpret_cast<float4 *>(smf + r * 2 * RS + 8 * c);
+                dst[0] = make_float4(a.x, b.x, a.y, b.y);
+                dst[1] = make_float4(a.z, b.z, a.w, b.w);
+            }
+        }
+    } else {
+        constexpr int CPR = N / 2;                      // 16-byte chunks (2 complex) per row
+        const float4 *z = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.in0) + row0 * 2 * N);
+#pragma unroll
+        for (int f = t; f < X * CPR; f += X) {
+            const int r = f / CPR, c = f % CPR;
+            if (r < rows) *reinterpret_cast<float4 *>(smf + r * 2 * RS + 4 * c) = ld_stream(z + f);
+        }
+    }
+    __syncthreads();
+
+    // ---- each thread: its own row -> registers -> transform -> back to its row
+    cx<R> x[N];
+    float4 *rowp = reinterpret_cast<float4 *>(smf + t * 2 * RS);
+    static_for<N / 2>([&](auto H_) {
+        CIDX(h, H_);
+        const float4 v = rowp[h];
+        x[2 * h] = mk<R>(v.x, v.y);
+        x[2 * h + 1] = mk<R>(v.z, v.w);
+    });
+    run_pass<R, PL, 0, INV>(x, tw, 0);
+    {
+        const float sc = (float)p.scale;
+        // register slot s holds element out_elem(s); emit adjacent element pairs as one STS.128
+        static_for<N>([&](auto S_) {
+            CIDX(sa, S_);
+            constexpr int ea = out_elem<PL, 0>(sa);
+            if constexpr (ea % 2 == 0) {
+                // find the slot holding element ea + 1
+                constexpr int sb = []() { for (int q = 0; q < N; q++) if (out_elem<PL, 0>(q) == ea + 1) return q; return -1; }();
+                float4 v = make_float4(x[sa].x, x[sa].y, x[sb].x, x[sb].y);
+                if (INV) v = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+                rowp[ea / 2] = v;
+            }
+        });
+    }
+    __syncthreads();
+
+    // ---- stage out
+    if constexpr (IO == IO_SPLIT) {
+        constexpr int CPR = N / 4;
+        float4 *re = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out0) + row0 * N);
+        float4 *im = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out1) + row0 * N);
+#pragma unroll
+        for (int f = t; f < X * CPR; f += X) {
+            const int r = f / CPR, c = f % CPR;
+            if (r < rows) {
+                const float4 *src = reinterpret_cast<const float4 *>(smf + r * 2 * RS + 8 * c);
+                const float4 u = src[0], v = src[1];
+                st_stream(re + f, make_float4(u.x, u.z, v.x, v.z));
+                st_stream(im + f, make_float4(u.y, u.w, v.y, v.w));
+            }
+        }
+    } else {
+        constexpr int CPR = N / 2;
+        float4 *z = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out0) + row0 * 2 * N);
+#pragma unroll
+        for (int f = t; f < X * CPR; f += X) {
+            const int r = f / CPR, c = f % CPR;
+            if (r < rows) st_stream(z + f, *reinterpret_cast<const float4 *>(smf + r * 2 * RS + 4 * c));
+        }
     }
 }
 
