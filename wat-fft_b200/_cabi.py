@@ -66,7 +66,7 @@ class WatFFTError(RuntimeError):
 
 def build(verbose: bool = False) -> Path:
     """nvcc -gencode arch=compute_100a,code=sm_100a -> wat-fft_b200/libwatfft_b200.so (in-tree)."""
-    subprocess.check_call(["make", "-C", str(HERE), "libwatfft_b200.so"],
+    subprocess.check_call(["make", "-C", str(HERE), "all"],
                           stdout=None if verbose else subprocess.DEVNULL)
     return LIB_PATH
 

@@ -4,12 +4,14 @@
 // [batch][row], optional pinned host staging buffers that the JS side wraps as ArrayBuffers, and a
 // stream.  There is no CPU path anywhere in this file: without an sm_100 device every call fails.
 #include "../../include/watfft_b200.h"
-#include "wfb_kernels.cuh"
+#include "wfb_registry.h"
 #include "wfb_twiddle.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -32,148 +34,54 @@ static int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 // ----------------------------------------------------------------------------------------
-// variant registry
+// kernel launch helpers (one launch counter and one attribute cache for the whole library)
 // ----------------------------------------------------------------------------------------
-typedef cudaError_t (*launch_fn)(int io, int dir, const KParams &p, long batch, cudaStream_t s);
+static std::mutex g_mu;
+static std::map<std::pair<int, const void *>, int> g_resident;   // (device, kernel) -> resident CTAs
 
-struct Variant {
-    const char *name;
-    int core_n;        // complex points of the core transform (n for C2C, n/2 for R2C)
-    int threads;       // per CTA
-    int rows_per_cta;  // X
-    size_t smem;       // dynamic shared memory per CTA
-    int lanes;         // batch rows per thread group: 2 for the packed-FP32 (f32x2) kernels
-    std::vector<int> radices;
-    launch_fn c2c, r2c, c2r;
-};
-
-template <class PL> static std::vector<int> plan_radices() {
-    std::vector<int> r;
-    for (int p = 0; p < PL::npass(); p++)
-        for (int q = 0; q < pass_nsub(PL::code(p)); q++) r.push_back(pass_radix(PL::code(p), q));
-    return r;
-}
-
-template <typename K> static cudaError_t launch_kernel(K kernel, size_t smem, int threads, long batch, int X,
-                                                       const KParams &p, cudaStream_t s) {
-    // `batch` here is the number of thread GROUPS (rows / lanes); X groups per CTA
-    // the dynamic-smem attribute is per (device, function); set it once for each pair
-    static std::mutex mu;
-    static std::set<std::pair<int, const void *>> configured;
+static cudaError_t configure(const void *kernel, size_t smem, int threads, int *resident) {
     int dev = 0;
     cudaGetDevice(&dev);
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        auto key = std::make_pair(dev, (const void *)kernel);
-        if (!configured.count(key)) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured.insert(key);
-        }
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto key = std::make_pair(dev, kernel);
+    auto it = g_resident.find(key);
+    if (it == g_resident.end()) {
+        // the dynamic-smem attribute is per (device, function); set it once for each pair
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1) per_sm = 1;
+        it = g_resident.emplace(key, per_sm * sms).first;
     }
-    long grid = (batch + X - 1) / X;
-    kernel<<<dim3((unsigned)grid), dim3(threads), smem, s>>>(p);
+    *resident = it->second;
+    return cudaSuccess;
+}
+
+cudaError_t launch_grid(const void *kernel, size_t smem, int threads, long ctas, const KParams &p, cudaStream_t s) {
+    if (!kernel) return cudaErrorInvalidDeviceFunction;
+    int resident;
+    cudaError_t e = configure(kernel, smem, threads, &resident);
+    if (e != cudaSuccess) return e;
+    void *args[] = {(void *)&p};
+    e = cudaLaunchKernel(kernel, dim3((unsigned)ctas), dim3(threads), args, smem, s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-constexpr int PADQ = 16;   // one pad slot per 16 complex values: conflict-free for every plan (tools/bank_sim.py)
-
-template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers {
-    static constexpr size_t smem = sizeof(cx<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
-    static constexpr int LANES = RT<R>::LANES;
-    static long groups(long batch) { return (batch + LANES - 1) / LANES; }
-    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
-        if constexpr (SPLIT_IO) {
-            if (io == IO_SPLIT) {
-                if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, true, MINB>, smem, PL::T * X, groups(batch), X, p, s);
-                return launch_kernel(k_c2c<R, PL, X, PADQ, IO_SPLIT, false, MINB>, smem, PL::T * X, groups(batch), X, p, s);
-            }
-        }
-        if (dir) return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB>, smem, PL::T * X, groups(batch), X, p, s);
-        return launch_kernel(k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB>, smem, PL::T * X, groups(batch), X, p, s);
-    }
-    static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_kernel(k_r2c<R, PL, X, PADQ, MINB>, smem, PL::T * X, groups(batch), X, p, s);
-    }
-    static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_kernel(k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, groups(batch), X, p, s);
-    }
-    static Variant make(const char *name) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, plan_radices<PL>(), &c2c, &r2c, &c2r};
-    }
-};
-
-template <class PL, int X, int MINB> struct TileLaunchers {
-    static constexpr size_t smem = sizeof(float) * 2 * (size_t)(PL::N + 2) * X;
-    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
-        if (io == IO_SPLIT) {
-            if (dir) return launch_kernel(k_c2c_tile<float, PL, X, IO_SPLIT, true, MINB>, smem, X, batch, X, p, s);
-            return launch_kernel(k_c2c_tile<float, PL, X, IO_SPLIT, false, MINB>, smem, X, batch, X, p, s);
-        }
-        if (dir) return launch_kernel(k_c2c_tile<float, PL, X, IO_INTERLEAVED, true, MINB>, smem, X, batch, X, p, s);
-        return launch_kernel(k_c2c_tile<float, PL, X, IO_INTERLEAVED, false, MINB>, smem, X, batch, X, p, s);
-    }
-    static Variant make(const char *name) {
-        return Variant{name, PL::N, X, X, smem, 1, plan_radices<PL>(), &c2c, nullptr, nullptr};
-    }
-};
-
-#define XROWS(T) ((T) >= 256 ? 1 : 256 / (T))
-
-// f32 core plans: the reference's split-core stage structure (radix-4, leading radix-2 for odd log2)
-using F32_4 = Plan<4, 1, 0x4>;
-using F32_8 = Plan<8, 1, 0x222>;
-using F32_16 = Plan<16, 1, 0x44>;
-using F32_32 = Plan<32, 2, 0x2, 0x44>;
-using F32_64 = Plan<64, 4, 0x4, 0x44>;
-using F32_128 = Plan<128, 8, 0x24, 0x44>;
-using F32_256 = Plan<256, 16, 0x44, 0x44>;
-using F32_512 = Plan<512, 32, 0x2, 0x44, 0x44>;
-using F32_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
-using F32_2048 = Plan<2048, 128, 0x24, 0x44, 0x44>;
-using F32_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
-using F32_8192 = Plan<8192, 512, 0x2, 0x44, 0x44, 0x44>;
-// thread-per-row plans for the tile kernels (whole transform in registers)
-using T32_32 = Plan<32, 1, 0x244>;
-using T32_64 = Plan<64, 1, 0x444>;
-// f64 core plans: radix-4 for N = 4^p, radix-2 otherwise (fft_combined.wat:727-732)
-using F64_4 = Plan<4, 1, 0x4>;
-using F64_8 = Plan<8, 1, 0x222>;
-using F64_16 = Plan<16, 1, 0x44>;
-using F64_32 = Plan<32, 2, 0x2, 0x2222>;
-using F64_64 = Plan<64, 4, 0x4, 0x44>;
-using F64_128 = Plan<128, 8, 0x222, 0x2222>;
-using F64_256 = Plan<256, 16, 0x44, 0x44>;
-using F64_512 = Plan<512, 32, 0x2, 0x2222, 0x2222>;
-using F64_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
-using F64_2048 = Plan<2048, 128, 0x222, 0x2222, 0x2222>;
-using F64_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
-using F64_8192 = Plan<8192, 512, 0x2, 0x2222, 0x2222, 0x2222>;
-
-#define V32(PL, MINB) Launchers<float, PL, XROWS(PL::T), MINB, true>::make(#PL)
-#define VTILE(PL, X, MINB) TileLaunchers<PL, X, MINB>::make(#PL "_tile")
-#define V32P(PL, MINB) Launchers<f32x2, PL, XROWS(PL::T), MINB, true>::make(#PL "_x2")
-#define V64(PL, MINB) Launchers<double, PL, XROWS(PL::T), MINB, false>::make(#PL)
-
-// Variant order = preference (variant 0 is the default).  "_x2" = packed FP32 lanes (two rows per
-// thread group, FFMA2/FADD2/FMUL2); the scalar variants stay selectable for comparison.
-static const std::vector<Variant> &variants_f32() {
-    static const std::vector<Variant> v = {
-        VTILE(F32_4, 256, 2), VTILE(F32_8, 256, 2), VTILE(F32_16, 256, 2), VTILE(T32_32, 128, 2), VTILE(T32_64, 128, 1),
-        V32(F32_4, 2), V32(F32_8, 2), V32(F32_16, 2), V32(F32_32, 2), V32(F32_64, 2), V32(F32_128, 2),
-        V32P(F32_256, 2), V32P(F32_512, 2), V32P(F32_1024, 2), V32P(F32_2048, 2), V32P(F32_4096, 2), V32P(F32_8192, 1),
-        V32P(F32_16, 2), V32P(F32_32, 2), V32P(F32_64, 2), V32P(F32_128, 2),
-        V32(F32_256, 2), V32(F32_512, 2), V32(F32_1024, 2), V32(F32_2048, 2), V32(F32_4096, 2), V32(F32_8192, 1),
-    };
-    return v;
-}
-static const std::vector<Variant> &variants_f64() {
-    static const std::vector<Variant> v = {
-        V64(F64_4, 2), V64(F64_8, 2), V64(F64_16, 2), V64(F64_32, 2), V64(F64_64, 2), V64(F64_128, 2),
-        V64(F64_256, 2), V64(F64_512, 2), V64(F64_1024, 2), V64(F64_2048, 2), V64(F64_4096, 1), V64(F64_8192, 1),
-    };
-    return v;
+// persistent kernels: grid = min(work items, CTAs resident on the whole GPU)
+cudaError_t launch_persistent(const void *kernel, size_t smem, int threads, long work_items, const KParams &p, cudaStream_t s) {
+    if (!kernel) return cudaErrorInvalidDeviceFunction;
+    int resident;
+    cudaError_t e = configure(kernel, smem, threads, &resident);
+    if (e != cudaSuccess) return e;
+    long grid = work_items < resident ? work_items : resident;
+    void *args[] = {(void *)&p};
+    e = cudaLaunchKernel(kernel, dim3((unsigned)grid), dim3(threads), args, smem, s);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -392,10 +300,15 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
     pl->core_n = (kind == WFB_R2C) ? n / 2 : n;
     pl->elem = precision == WFB_F64 ? 8 : 4;
     pl->variant = 0;
-    const std::vector<Variant> &all = precision == WFB_F64 ? variants_f64() : variants_f32();
-    for (const Variant &v : all)
-        if (v.core_n == pl->core_n && pl->variants.size() < 8 && (kind == WFB_C2C ? v.c2c != nullptr : v.r2c != nullptr))
-            pl->variants.push_back(&v);
+    std::vector<const std::vector<Variant> *> families;
+    if (precision == WFB_F64) families = {&variants_f64()};
+    else families = {&variants_f32_tile(), &variants_f32_pipe(), &variants_f32_x2(), &variants_f32_direct()};
+    for (const auto *fam : families)
+        for (const Variant &v : *fam)
+            if (v.core_n == pl->core_n && (kind == WFB_C2C ? v.c2c != nullptr : v.r2c != nullptr)) pl->variants.push_back(&v);
+    std::stable_sort(pl->variants.begin(), pl->variants.end(),
+                     [](const Variant *a, const Variant *b) { return a->priority > b->priority; });
+    if (pl->variants.size() > 8) pl->variants.resize(8);
     if (pl->variants.empty()) { *err = WFB_ERR_BAD_SIZE; delete pl; return nullptr; }
     *err = plan_init(pl);
     if (*err) { wfb_plan_destroy(pl); return nullptr; }

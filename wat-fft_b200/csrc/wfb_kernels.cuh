@@ -715,4 +715,153 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tile(KParams p) {
     }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// TMA-pipelined persistent c2c (large N).  Each CTA owns T threads and loops over its transforms;
+// an elected thread streams the NEXT transform's rows into shared memory with cp.async.bulk (the
+// TMA engine; SASS UBLKCP) while the CTA computes the current one, completion signalled on an
+// mbarrier.  The global->smem traffic therefore never occupies registers or LSU issue slots and
+// there is always one transform per resident CTA in flight -- the one-CTA-one-transform kernel
+// above alternates load and compute phases and left ~30 % of the HBM roofline idle at N = 4096.
+// The two stage buffers double as the exchange scratch of the transform being computed.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr size_t pipe_buf_bytes() {
+    size_t a = sizeof(cx<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
+    return (a + 127) / 128 * 128;
+}
+
+template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB>
+__global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
+    static_assert(PL::valid(), "plan does not factor N");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using S = typename VecOf<R>::s;
+    using V2 = typename VecOf<R>::v2;
+    constexpr int LANES = RT<R>::LANES;
+    constexpr int N = PL::N;
+    constexpr int LAST = PL::npass() - 1;
+    constexpr int ROWS = X * LANES;                 // rows per CTA iteration (one dense tile)
+    constexpr size_t BUF = pipe_buf_bytes<R, PL, PADQ, X>();
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
+    const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+    const long tiles = (p.batch + ROWS - 1) / ROWS;
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar + 0, 1);
+        mbar_init(mbar + 1, 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    auto issue = [&](long tile, int st) {       // elected thread: stream the tile's rows into stage st
+        const long row = tile * ROWS;
+        const int rows = (p.batch - row < ROWS) ? (int)(p.batch - row) : ROWS;
+        unsigned char *dst = smem_raw + st * BUF;
+        if constexpr (IO == IO_SPLIT) {
+            const uint32_t bytes = (uint32_t)(rows * N * sizeof(S));
+            mbar_expect_tx(mbar + st, 2 * bytes);
+            tma_load_1d(dst, reinterpret_cast<const S *>(p.in0) + row * N, bytes, mbar + st);
+            tma_load_1d(dst + ROWS * N * sizeof(S), reinterpret_cast<const S *>(p.in1) + row * N, bytes, mbar + st);
+        } else {
+            const uint32_t bytes = (uint32_t)(rows * N * 2 * sizeof(S));
+            mbar_expect_tx(mbar + st, bytes);
+            tma_load_1d(dst, reinterpret_cast<const S *>(p.in0) + row * 2 * N, bytes, mbar + st);
+        }
+    };
+
+    long tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < tiles) issue(tile, 0);
+    cx<R> x[PL::E];
+    for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
+        const int st = it & 1;
+        fence_proxy_async();      // our generic-proxy accesses to the other stage precede its refill
+        __syncthreads();          // ... and everyone is done using it as scratch
+        if (threadIdx.x == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        mbar_wait(mbar + st, (it >> 1) & 1);
+
+        const long row = tile * ROWS + (long)xi * LANES;
+        const bool active = row < p.batch;
+        const bool two = LANES == 2 && row + 1 < p.batch;
+        unsigned char *buf = smem_raw + st * BUF;
+        if constexpr (IO == IO_SPLIT) {
+            const S *re = reinterpret_cast<const S *>(buf) + (size_t)xi * LANES * N + tid;
+            const S *im = re + ROWS * N;
+            static_for<PL::E>([&](auto E_) {
+                CIDX(e, E_);
+                if constexpr (LANES == 2) {
+                    x[e].x.v = make_float2(re[e * PL::T], re[N + e * PL::T]);
+                    x[e].y.v = make_float2(im[e * PL::T], im[N + e * PL::T]);
+                } else {
+                    x[e] = mk<R>(re[e * PL::T], im[e * PL::T]);
+                }
+            });
+        } else {
+            const V2 *z = reinterpret_cast<const V2 *>(buf) + (size_t)xi * LANES * N + tid;
+            static_for<PL::E>([&](auto E_) {
+                CIDX(e, E_);
+                if constexpr (LANES == 2) {
+                    const V2 a = z[e * PL::T], b = z[N + e * PL::T];
+                    x[e].x.v = make_float2(a.x, b.x);
+                    x[e].y.v = make_float2(a.y, b.y);
+                } else {
+                    const V2 a = z[e * PL::T];
+                    x[e] = mk<R>(a.x, a.y);
+                }
+            });
+        }
+        // the dense input tile and the padded per-group scratch regions alias: every group must
+        // have its inputs in registers before any group spills
+        if constexpr (PL::npass() > 1) __syncthreads();
+        cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(N);
+        run_all<R, PL, PADQ, X, INV>(x, tw, scratch, tid, xi, false);
+
+        if (active) {
+            const long rs = two ? N : 0;
+            const R sc = RT<R>::splat((S)p.scale);
+            if constexpr (IO == IO_SPLIT) {
+                S *re = reinterpret_cast<S *>(p.out0) + row * N + tid;
+                S *im = reinterpret_cast<S *>(p.out1) + row * N + tid;
+                static_for<PL::E>([&](auto S_) {
+                    CIDX(slot, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot);
+                    cx<R> v = x[slot];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    GIO<R>::st_split(re + e * PL::T, im + e * PL::T, rs, two, v);
+                });
+            } else {
+                V2 *z = reinterpret_cast<V2 *>(p.out0) + row * N + tid;
+                static_for<PL::E>([&](auto S_) {
+                    CIDX(slot, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot);
+                    cx<R> v = x[slot];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    GIO<R>::st_il(z + e * PL::T, rs, two, v);
+                });
+            }
+        }
+    }
+}
+
 }  // namespace wfb

@@ -1,0 +1,143 @@
+// wfb_registry.h -- kernel-variant registry shared by the variant translation units and the API.
+//
+// Each wfb_variants_*.cu instantiates a family of kernels and returns descriptors (Variant); the
+// API (wfb_api.cu) picks, per (precision, core size, kind), the variant with the highest priority
+// as the plan's default and keeps the others selectable (wfb_plan_set_variant) for tuning.
+#pragma once
+#include "wfb_kernels.cuh"
+
+#include <vector>
+
+namespace wfb {
+
+typedef cudaError_t (*launch_fn)(int io, int dir, const KParams &p, long batch, cudaStream_t s);
+
+struct Variant {
+    const char *name;
+    int core_n;        // complex points of the core transform (n for C2C, n/2 for R2C)
+    int threads;       // per CTA
+    int rows_per_cta;  // thread groups per CTA
+    size_t smem;       // dynamic shared memory per CTA
+    int lanes;         // batch rows per thread group: 2 for the packed-FP32 (f32x2) kernels
+    int priority;      // larger = preferred default (set from measurements, profiles/)
+    std::vector<int> radices;
+    launch_fn c2c, r2c, c2r;
+};
+
+// implemented in wfb_api.cu (one launch counter / attribute cache for the whole library)
+cudaError_t launch_grid(const void *kernel, size_t smem, int threads, long ctas, const KParams &p, cudaStream_t s);
+cudaError_t launch_persistent(const void *kernel, size_t smem, int threads, long work_items, const KParams &p, cudaStream_t s);
+
+const std::vector<Variant> &variants_f32_direct();
+const std::vector<Variant> &variants_f32_x2();
+const std::vector<Variant> &variants_f32_tile();
+const std::vector<Variant> &variants_f32_pipe();
+const std::vector<Variant> &variants_f64();
+
+template <class PL> std::vector<int> plan_radices() {
+    std::vector<int> r;
+    for (int p = 0; p < PL::npass(); p++)
+        for (int q = 0; q < pass_nsub(PL::code(p)); q++) r.push_back(pass_radix(PL::code(p), q));
+    return r;
+}
+
+constexpr int PADQ = 16;   // one pad slot per 16 complex values: conflict-free for every plan (tools/bank_sim.py)
+
+// one transform (or lane pair) per thread group, X groups per CTA, direct global loads/stores
+template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers {
+    static constexpr size_t smem = sizeof(cx<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
+    static constexpr int LANES = RT<R>::LANES;
+    static long ctas(long batch) { return ((batch + LANES - 1) / LANES + X - 1) / X; }
+    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
+        const void *k;
+        if (SPLIT_IO && io == IO_SPLIT) {
+            if constexpr (SPLIT_IO)
+                k = dir ? (const void *)k_c2c<R, PL, X, PADQ, IO_SPLIT, true, MINB> : (const void *)k_c2c<R, PL, X, PADQ, IO_SPLIT, false, MINB>;
+            else
+                k = nullptr;
+        } else {
+            k = dir ? (const void *)k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB>;
+        }
+        return launch_grid(k, smem, PL::T * X, ctas(batch), p, s);
+    }
+    static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_grid((const void *)k_r2c<R, PL, X, PADQ, MINB>, smem, PL::T * X, ctas(batch), p, s);
+    }
+    static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_grid((const void *)k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, ctas(batch), p, s);
+    }
+    static Variant make(const char *name, int priority) {
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, plan_radices<PL>(), &c2c, &r2c, &c2r};
+    }
+};
+
+// persistent TMA-pipelined c2c: grid = resident CTAs, each loops over tiles of X*LANES rows
+template <typename R, class PL, int X, int MINB> struct PipeLaunchers {
+    static constexpr size_t smem = 2 * pipe_buf_bytes<R, PL, PADQ, X>() + 64;
+    static constexpr int LANES = RT<R>::LANES;
+    static long tiles(long batch) { return (batch + X * LANES - 1) / (X * LANES); }
+    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
+        const void *k;
+        if (io == IO_SPLIT)
+            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_SPLIT, true, MINB> : (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_SPLIT, false, MINB>;
+        else
+            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB>;
+        return launch_persistent(k, smem, PL::T * X, tiles(batch), p, s);
+    }
+    static Variant make(const char *name, int priority) {
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    }
+};
+
+// thread-per-row tile kernels (N <= 64)
+template <class PL, int X, int MINB> struct TileLaunchers {
+    static constexpr size_t smem = sizeof(float) * 2 * (size_t)(PL::N + 2) * X;
+    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
+        const void *k;
+        if (io == IO_SPLIT)
+            k = dir ? (const void *)k_c2c_tile<float, PL, X, IO_SPLIT, true, MINB> : (const void *)k_c2c_tile<float, PL, X, IO_SPLIT, false, MINB>;
+        else
+            k = dir ? (const void *)k_c2c_tile<float, PL, X, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_tile<float, PL, X, IO_INTERLEAVED, false, MINB>;
+        return launch_grid(k, smem, X, (batch + X - 1) / X, p, s);
+    }
+    static Variant make(const char *name, int priority) {
+        return Variant{name, PL::N, X, X, smem, 1, priority, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    }
+};
+
+#define XROWS(T) ((T) >= 256 ? 1 : 256 / (T))
+
+// f32 core plans: the reference's split-core stage structure (radix-4, leading radix-2 for odd log2)
+using F32_4 = Plan<4, 1, 0x4>;
+using F32_8 = Plan<8, 1, 0x222>;
+using F32_16 = Plan<16, 1, 0x44>;
+using F32_32 = Plan<32, 2, 0x2, 0x44>;
+using F32_64 = Plan<64, 4, 0x4, 0x44>;
+using F32_128 = Plan<128, 8, 0x24, 0x44>;
+using F32_256 = Plan<256, 16, 0x44, 0x44>;
+using F32_512 = Plan<512, 32, 0x2, 0x44, 0x44>;
+using F32_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
+using F32_2048 = Plan<2048, 128, 0x24, 0x44, 0x44>;
+using F32_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
+using F32_8192 = Plan<8192, 512, 0x2, 0x44, 0x44, 0x44>;
+// experimental: 32 values per thread (two register blocks per pass), half the threads per transform
+using P32_4096_T128 = Plan<4096, 128, 0x44, 0x44, 0x44>;
+using P32_2048_T64 = Plan<2048, 64, 0x24, 0x44, 0x44>;
+// thread-per-row plans for the tile kernels (whole transform in registers)
+using T32_32 = Plan<32, 1, 0x244>;
+using T32_64 = Plan<64, 1, 0x444>;
+// f64 core plans: radix-4 for N = 4^p, radix-2 otherwise (fft_combined.wat:727-732)
+using F64_4 = Plan<4, 1, 0x4>;
+using F64_8 = Plan<8, 1, 0x222>;
+using F64_16 = Plan<16, 1, 0x44>;
+using F64_32 = Plan<32, 2, 0x2, 0x2222>;
+using F64_64 = Plan<64, 4, 0x4, 0x44>;
+using F64_128 = Plan<128, 8, 0x222, 0x2222>;
+using F64_256 = Plan<256, 16, 0x44, 0x44>;
+using F64_512 = Plan<512, 32, 0x2, 0x2222, 0x2222>;
+using F64_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
+using F64_2048 = Plan<2048, 128, 0x222, 0x2222, 0x2222>;
+using F64_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
+using F64_8192 = Plan<8192, 512, 0x2, 0x2222, 0x2222, 0x2222>;
+
+}  // namespace wfb

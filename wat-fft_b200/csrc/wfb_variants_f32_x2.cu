@@ -1,0 +1,11 @@
+// packed-FP32 (f32x2: FFMA2/FADD2/FMUL2) kernels, two batch rows per thread group
+#include "wfb_registry.h"
+namespace wfb {
+#define V(PL, MINB, PRIO) Launchers<f32x2, PL, XROWS(PL::T), MINB, true>::make(#PL "_x2", PRIO)
+const std::vector<Variant> &variants_f32_x2() {
+    static const std::vector<Variant> v = {
+        V(F32_128, 2, 20), V(F32_256, 2, 20), V(F32_512, 2, 20), V(F32_1024, 2, 20), V(F32_2048, 2, 5), V(F32_4096, 2, 5),
+    };
+    return v;
+}
+}  // namespace wfb
