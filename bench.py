@@ -231,10 +231,14 @@ def run_ours(args):
         if events is not None:
             events[2 * len(SIZES)].record(stream)
 
+    sampler = ClockSampler(local) if rank == 0 else None     # nvidia-smi needs ~0.3 s to start sampling
     for _ in range(max(3, args.warmup)):
         step()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.5:                    # keep the GPU under load until the sampler is live
+        step()
+        torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.wfb_kernel_launch_count()
     K = args.steps
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * len(SIZES) + 1)] for _ in range(K)]
@@ -349,7 +353,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

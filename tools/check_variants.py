@@ -50,5 +50,51 @@ for n in sizes:
                 row.append(f"{vn}{'/il' if layout else ''}{'/inv' if inv else ''}:{'ok' if ok else 'FAIL %.2e' % worst}")
         plan.destroy()
     print(n, " ".join(row), flush=True)
+# real transforms and f64: every variant against the oracle
+for n in sizes:
+    b = 37 if n <= 1024 else 7
+    row = []
+    if n >= 32:
+        x = rng.uniform(-1, 1, (b, n)).astype(np.float32)
+        spec = np.stack([O.rfft_split_f32(x[r]) for r in range(b)])
+        plan = wf.Plan(C.R2C, C.F32, 0, n, b)
+        for vi, vn in enumerate(plan.variants()):
+            plan.set_variant(vi)
+            plan.host(C.BUF_TIME)[:] = x.ravel(); plan.exec(C.FORWARD)
+            g = plan.host(C.BUF_SPECTRUM).reshape(b, n + 2)
+            w1 = max(rel(g[r], spec[r], x[r]) for r in range(b))
+            plan.host(C.BUF_SPECTRUM)[:] = spec.ravel(); plan.exec(C.INVERSE)
+            t = plan.host(C.BUF_TIME).reshape(b, n)
+            w2 = max(rel(t[r], O.irfft_split_f32(spec[r]), spec[r]) for r in range(b))
+            ok = max(w1, w2) <= 2e-6 * math.log2(n); bad += (not ok)
+            row.append(f"r2c:{vn}:{'ok' if ok else 'FAIL %.2e %.2e' % (w1, w2)}")
+        plan.destroy()
+    d = rng.uniform(-1, 1, (b, 2 * n))
+    if n <= 8192:
+        plan = wf.Plan(C.C2C, C.F64, C.INTERLEAVED, n, b)
+        for vi, vn in enumerate(plan.variants()):
+            plan.set_variant(vi)
+            w = 0.0
+            for inv in (False, True):
+                plan.host(0)[:] = d.ravel(); plan.exec(C.INVERSE if inv else C.FORWARD)
+                g = plan.host(0).reshape(b, 2 * n)
+                w = max(w, max(rel(g[r], O.fft_f64(d[r], inv), d[r]) for r in range(b)))
+            ok = w <= 1e-14 * math.log2(n); bad += (not ok)
+            row.append(f"f64:{vn}:{'ok' if ok else 'FAIL %.2e' % w}")
+        plan.destroy()
+    if n >= 8:
+        x = rng.uniform(-1, 1, (b, n))
+        plan = wf.Plan(C.R2C, C.F64, 0, n, b)
+        for vi, vn in enumerate(plan.variants()):
+            plan.set_variant(vi)
+            plan.host(C.BUF_TIME)[:] = x.ravel(); plan.exec(C.FORWARD)
+            g = plan.host(C.BUF_SPECTRUM).reshape(b, n + 2).copy()
+            w = max(rel(g[r], O.rfft_f64(x[r]), x[r]) for r in range(b))
+            plan.exec(C.INVERSE)
+            rt = float(np.max(np.abs(plan.host(C.BUF_TIME).reshape(b, n) - x)))
+            ok = w <= 1e-14 * math.log2(n) and rt < 1e-9; bad += (not ok)
+            row.append(f"r2c64:{vn}:{'ok' if ok else 'FAIL %.2e rt %.2e' % (w, rt)}")
+        plan.destroy()
+    print(n, " ".join(row), flush=True)
 print("FAILURES:", bad)
 sys.exit(1 if bad else 0)

@@ -49,6 +49,8 @@ static cudaError_t configure(const void *kernel, size_t smem, int threads, int *
         // the dynamic-smem attribute is per (device, function); set it once for each pair
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // NOTE: forcing cudaSharedmemCarveoutMaxShared was measured (gpurun sweep9) to LOSE 5-15 %: it shrinks
+        // L1, which the twiddle tables and the direct-load kernels live in.  The driver's default split stays.
         int per_sm = 0, sms = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
         if (e != cudaSuccess) return e;
@@ -301,8 +303,8 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
     pl->elem = precision == WFB_F64 ? 8 : 4;
     pl->variant = 0;
     std::vector<const std::vector<Variant> *> families;
-    if (precision == WFB_F64) families = {&variants_f64()};
-    else families = {&variants_f32_tile(), &variants_f32_pipe(), &variants_f32_x2(), &variants_f32_direct()};
+    if (precision == WFB_F64) families = {&variants_f64_pipe(), &variants_f64()};
+    else families = {&variants_f32_tile(), &variants_f32_pipe(), &variants_f32_real_pipe(), &variants_f32_x2(), &variants_f32_direct()};
     for (const auto *fam : families)
         for (const Variant &v : *fam)
             if (v.core_n == pl->core_n && (kind == WFB_C2C ? v.c2c != nullptr : v.r2c != nullptr)) pl->variants.push_back(&v);

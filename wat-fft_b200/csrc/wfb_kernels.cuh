@@ -864,4 +864,164 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
     }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// TMA-pipelined persistent r2c / c2r (scalar lanes).  Same pipeline as k_c2c_pipe: the next tile
+// of X rows is streamed into shared memory while the current one is transformed.
+//   r2c: rows of N reals are read as M = N/2 complex values; the Hermitian post-process runs out
+//        of the group's scratch into coalesced 8-byte stores of the (M+1)-bin rows.
+//   c2r: rows are (M+1) complex values (8-byte aligned only), so tiles hold an even number of rows
+//        (16-byte aligned starts and sizes); an odd-sized last tile is copied by the threads.
+// ----------------------------------------------------------------------------------------
+template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ constexpr size_t real_pipe_buf_bytes() {
+    size_t scratch = sizeof(cx<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
+    size_t raw = sizeof(cx<R>) * (size_t)(C2R ? PL::N + 1 : PL::N) * X;
+    size_t a = scratch > raw ? scratch : raw;
+    return (a + 127) / 128 * 128;
+}
+
+template <typename R, class PL, int X, int PADQ, bool C2R, int MINB>
+__global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
+    static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
+    static_assert(!C2R || X % 2 == 0, "c2r tiles need an even number of rows (16-byte alignment)");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using S = typename VecOf<R>::s;
+    using V2 = typename VecOf<R>::v2;
+    constexpr int M = PL::N;
+    constexpr int LAST = PL::npass() - 1;
+    constexpr int IN_ROW = C2R ? M + 1 : M;          // row lengths in complex values
+    constexpr size_t BUF = real_pipe_buf_bytes<R, PL, PADQ, X, C2R>();
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
+    const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+    const typename RT<R>::twel *rtw = reinterpret_cast<const typename RT<R>::twel *>(p.rtw);
+    const long tiles = (p.batch + X - 1) / X;
+    const V2 *gin = reinterpret_cast<const V2 *>(p.in0);
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar + 0, 1);
+        mbar_init(mbar + 1, 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    auto tile_rows = [&](long tile) { const long row = tile * X; return (p.batch - row < X) ? (int)(p.batch - row) : X; };
+    auto tma_ok = [&](long tile) { return !C2R || (tile_rows(tile) % 2 == 0); };
+    auto issue = [&](long tile, int st) {
+        if (!tma_ok(tile)) return;
+        const uint32_t bytes = (uint32_t)(tile_rows(tile) * IN_ROW * sizeof(V2));
+        mbar_expect_tx(mbar + st, bytes);
+        tma_load_1d(smem_raw + st * BUF, gin + tile * X * IN_ROW, bytes, mbar + st);
+    };
+
+    long tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < tiles) issue(tile, 0);
+    cx<R> x[PL::E];
+    unsigned phasebits = 0;                            // mbarrier phase parity per stage (bit st)
+    for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
+        const int st = it & 1;
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        unsigned char *buf = smem_raw + st * BUF;
+        if (tma_ok(tile)) {
+            mbar_wait(mbar + st, (phasebits >> st) & 1u);
+            phasebits ^= 1u << st;
+        } else {                                       // odd-sized last c2r tile: plain cooperative copy
+            const int count = tile_rows(tile) * IN_ROW;
+            V2 *dst = reinterpret_cast<V2 *>(buf);
+            for (int i = threadIdx.x; i < count; i += PL::T * X) dst[i] = ld_stream(gin + tile * X * IN_ROW + i);
+            __syncthreads();
+        }
+        const long row = tile * X + xi;
+        const bool active = row < p.batch;
+        cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(M);
+        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xi * IN_ROW;
+
+        if constexpr (!C2R) {
+            // ---------------- r2c
+            static_for<PL::E>([&](auto E_) { CIDX(e, E_); const V2 a = raw[tid + e * PL::T]; x[e] = mk<R>(a.x, a.y); });
+            __syncthreads();                           // dense tile and padded scratch alias
+            run_all<R, PL, PADQ, X, false>(x, tw, scratch, tid, xi, false);
+            if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
+            spill_outputs<R, PL, LAST, PADQ>(x, scratch, tid);
+            sync_transform<PL::T, X>(xi);
+            if (active) {
+                V2 *out = reinterpret_cast<V2 *>(p.out0) + row * (M + 1);
+                constexpr int HALF = M / 2;
+                constexpr int PER = (HALF + PL::T - 1) / PL::T;
+                const R zero = RT<R>::splat(0);
+                static_for<PER>([&](auto I_) {
+                    CIDX(i, I_);
+                    const int k = tid + i * PL::T;
+                    if (k < HALF) {
+                        if (i == 0 && k == 0) {
+                            const cx<R> z0 = scratch[0];
+                            GIO<R>::st_il(out, 0, false, mk<R>(radd(z0.x, z0.y), zero));
+                            GIO<R>::st_il(out + M, 0, false, mk<R>(rsub(z0.x, z0.y), zero));
+                            const cx<R> zh = scratch[pad_idx<PADQ>(HALF)];
+                            GIO<R>::st_il(out + HALF, 0, false, RealPost<R>::middle(zh, ld_tw(rtw + HALF), M));
+                        } else {
+                            const cx<R> z = scratch[pad_idx<PADQ>(k)], zm = scratch[pad_idx<PADQ>(M - k)];
+                            cx<R> xk, xm;
+                            RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);
+                            GIO<R>::st_il(out + k, 0, false, xk);
+                            GIO<R>::st_il(out + (M - k), 0, false, xm);
+                        }
+                    }
+                });
+            }
+        } else {
+            // ---------------- c2r: Hermitian pre-process into registers, then through the scratch
+            constexpr int HALF = M / 2;
+            constexpr int PER = (HALF + PL::T - 1) / PL::T;
+            static_assert(2 * PER <= PL::E, "pre-process registers");
+            const R sc = RT<R>::splat(S(0.5) / S(M));
+            cx<R> z0 = mk<R>(RT<R>::splat(0), RT<R>::splat(0));
+            static_for<PER>([&](auto I_) {
+                CIDX(i, I_);
+                const int k = tid + i * PL::T;
+                if (k < HALF) {
+                    if (i == 0 && k == 0) {
+                        const V2 a0 = raw[0], am = raw[M];          // real parts only (:1679-1684)
+                        z0 = mk<R>(rmul(radd(a0.x, am.x), sc), rmul(rsub(a0.x, am.x), sc));
+                    }
+                    const int kk = (k == 0) ? HALF : k;
+                    const V2 a = raw[kk], b = raw[M - kk];
+                    const twd<R> w = ld_tw(rtw + kk);
+                    const R gr = radd(a.x, b.x), gi = rsub(a.y, b.y), ur = rsub(a.x, b.x), ui = radd(a.y, b.y);
+                    const R hr = rfma(w.y, ui, rmul(w.x, ur)), hi = rfma(w.ny, ur, rmul(w.x, ui));
+                    x[2 * i] = mk<R>(rmul(sc, rsub(gr, hi)), rmul(sc, radd(gi, hr)));
+                    x[2 * i + 1] = mk<R>(rmul(sc, radd(gr, hi)), rmul(sc, rsub(hr, gi)));
+                }
+            });
+            __syncthreads();                           // every group has consumed its raw rows
+            static_for<PER>([&](auto I_) {
+                CIDX(i, I_);
+                const int k = tid + i * PL::T;
+                if (k < HALF) {
+                    if (i == 0 && k == 0) scratch[0] = z0;
+                    const int kk = (k == 0) ? HALF : k;
+                    scratch[pad_idx<PADQ>(kk)] = x[2 * i];          // forward first, mirrored second (:1722-1740)
+                    scratch[pad_idx<PADQ>(M - kk)] = x[2 * i + 1];
+                }
+            });
+            sync_transform<PL::T, X>(xi);
+            {
+                const cx<R> *base = scratch + pad_idx<PADQ>(tid);
+                static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = base[pad_off<PADQ>(e * PL::T)]; });
+            }
+            run_all<R, PL, PADQ, X, true>(x, tw, scratch, tid, xi, true);
+            if (active) {
+                V2 *z = reinterpret_cast<V2 *>(p.out0) + row * M + tid;
+                static_for<PL::E>([&](auto S_) {
+                    CIDX(slot, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot);
+                    GIO<R>::st_il(z + e * PL::T, 0, false, x[slot]);
+                });
+            }
+        }
+    }
+}
+
 }  // namespace wfb

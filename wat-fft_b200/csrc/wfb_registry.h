@@ -33,6 +33,8 @@ const std::vector<Variant> &variants_f32_x2();
 const std::vector<Variant> &variants_f32_tile();
 const std::vector<Variant> &variants_f32_pipe();
 const std::vector<Variant> &variants_f64();
+const std::vector<Variant> &variants_f32_real_pipe();
+const std::vector<Variant> &variants_f64_pipe();
 
 template <class PL> std::vector<int> plan_radices() {
     std::vector<int> r;
@@ -86,6 +88,21 @@ template <typename R, class PL, int X, int MINB> struct PipeLaunchers {
     }
     static Variant make(const char *name, int priority) {
         return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    }
+};
+
+// persistent TMA-pipelined r2c / c2r (scalar lanes)
+template <typename R, class PL, int X, int MINB> struct RealPipeLaunchers {
+    static constexpr size_t smem_f = 2 * real_pipe_buf_bytes<R, PL, PADQ, X, false>() + 64;
+    static constexpr size_t smem_i = 2 * real_pipe_buf_bytes<R, PL, PADQ, X, true>() + 64;
+    static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_persistent((const void *)k_real_pipe<R, PL, X, PADQ, false, MINB>, smem_f, PL::T * X, (batch + X - 1) / X, p, s);
+    }
+    static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_persistent((const void *)k_real_pipe<R, PL, X, PADQ, true, MINB>, smem_i, PL::T * X, (batch + X - 1) / X, p, s);
+    }
+    static Variant make(const char *name, int priority) {
+        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 
