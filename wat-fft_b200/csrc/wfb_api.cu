@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -113,7 +114,7 @@ struct wfb_plan {
     cudaStream_t stream;
     // staging pipeline: chunks of rows cycle over these streams so the H2D copy of chunk c+1, the
     // kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex)
-    enum { NPIPE = 3 };
+    enum { NPIPE = 6 };
     cudaStream_t pipe[NPIPE];
     cudaEvent_t pipe_done[NPIPE], start_ev;
 };
@@ -426,7 +427,9 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
     // rows per pipeline chunk: ~16 MiB of the widest plane, so each copy is long enough to run at
     // full PCIe rate while there are enough chunks to overlap the two directions
     size_t widest = src_row[0] > dst_row[0] ? src_row[0] : dst_row[0];
-    long chunk = (long)((16u << 20) / widest);
+    static const long chunk_bytes = [] { const char *e = getenv("WFB_STAGE_CHUNK_MB"); long v = e ? atol(e) : 32; return (v < 1 ? 1 : v) << 20; }();
+    static const int nstreams = [] { const char *e = getenv("WFB_STAGE_STREAMS"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > wfb_plan::NPIPE ? (int)wfb_plan::NPIPE : v); }();
+    long chunk = (long)(chunk_bytes / (long)widest);
     if (chunk < 1) chunk = 1;
     const bool pipelined = (h2d || d2h) && pl->batch > 2 * chunk;
     if (!pipelined) {
@@ -446,7 +449,7 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
         int c = 0;
         for (long r0 = 0; r0 < pl->batch; r0 += chunk, c++) {
             const long rows = (pl->batch - r0 < chunk) ? pl->batch - r0 : chunk;
-            cudaStream_t s = pl->pipe[c % wfb_plan::NPIPE];
+            cudaStream_t s = pl->pipe[c % nstreams];
             char *di[2] = {nullptr, nullptr}, *dout[2] = {nullptr, nullptr};
             for (int i = 0; i < 2; i++) {
                 if (src[i] >= 0) {

@@ -186,6 +186,28 @@ template <class PL, int P> __host__ __device__ constexpr int out_elem(int slot) 
     return (slot % NB) + NB * slot_to_out(PL::code(P), slot / NB);
 }
 
+// First half of a twiddled radix-4 butterfly: t0 = A + w2*C, t1 = A - w2*C, t2 = w1*B + w3*D,
+// t3 = w1*B - w3*D  (fft_split_native_f32.wat:826-848).  Generic form: three products, four add/subs.
+template <typename R>
+__device__ __forceinline__ void twiddled_r4(const cx<R> &A, const cx<R> &B, const cx<R> &C, const cx<R> &D,
+                                            const twd<R> &w1, const twd<R> &w2, const twd<R> &w3,
+                                            cx<R> &t0, cx<R> &t1, cx<R> &t2, cx<R> &t3) {
+    const cx<R> wb = cmul<R>(w1, B), wc = cmul<R>(w2, C), wd = cmul<R>(w3, D);
+    t0 = cadd<R>(A, wc); t1 = csub<R>(A, wc);
+    t2 = cadd<R>(wb, wd); t3 = csub<R>(wb, wd);
+}
+// f32 scalar lanes: FMA-fused form, 16 instead of 20 instructions (negated operands are free SASS
+// modifiers): t0 and t2 as FMA chains, then t1 = 2A - t0 and t3 = 2*(w1*B) - t2.
+__device__ __forceinline__ void twiddled_r4(const cx<float> &A, const cx<float> &B, const cx<float> &C, const cx<float> &D,
+                                            const twd<float> &w1, const twd<float> &w2, const twd<float> &w3,
+                                            cx<float> &t0, cx<float> &t1, cx<float> &t2, cx<float> &t3) {
+    const cx<float> wb = cmul<float>(w1, B);
+    t0 = mk<float>(fmaf(w2.ny, C.y, fmaf(w2.x, C.x, A.x)), fmaf(w2.y, C.x, fmaf(w2.x, C.y, A.y)));
+    t2 = mk<float>(fmaf(w3.ny, D.y, fmaf(w3.x, D.x, wb.x)), fmaf(w3.y, D.x, fmaf(w3.x, D.y, wb.y)));
+    t1 = mk<float>(fmaf(2.0f, A.x, -t0.x), fmaf(2.0f, A.y, -t0.y));
+    t3 = mk<float>(fmaf(2.0f, wb.x, -t2.x), fmaf(2.0f, wb.y, -t2.y));
+}
+
 // ----------------------------------------------------------------------------------------
 // one fused pass over the E register-resident values of a thread
 // ----------------------------------------------------------------------------------------
@@ -236,10 +258,13 @@ __device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>
                     } else {
                         cx<R> &A = x[i + NB * k0], &B = x[i + NB * (k0 + w)];
                         cx<R> &C = x[i + NB * (k0 + 2 * w)], &D = x[i + NB * (k0 + 3 * w)];
-                        cx<R> wb = B, wc = C, wd = D;
-                        if constexpr (!unit) { wb = cmul<R>(w1, B); wc = cmul<R>(w2, C); wd = cmul<R>(w3, D); }
-                        const cx<R> t0 = cadd<R>(A, wc), t1 = csub<R>(A, wc);
-                        const cx<R> t2 = cadd<R>(wb, wd), t3 = csub<R>(wb, wd);
+                        cx<R> t0, t1, t2, t3;
+                        if constexpr (unit) {
+                            t0 = cadd<R>(A, C); t1 = csub<R>(A, C);
+                            t2 = cadd<R>(B, D); t3 = csub<R>(B, D);
+                        } else {
+                            twiddled_r4(A, B, C, D, w1, w2, w3, t0, t1, t2, t3);
+                        }
                         A = cadd<R>(t0, t2);
                         C = csub<R>(t0, t2);
                         // forward: out1 = t1 - i*t3, out3 = t1 + i*t3; the inverse swaps them
@@ -794,6 +819,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
     long tile = blockIdx.x;
     if (threadIdx.x == 0 && tile < tiles) issue(tile, 0);
     cx<R> x[PL::E];
+    // (hoisting the last pass's thread-invariant twiddles into registers was tried and measured
+    //  neutral at N = 4096 and 3-6 % slower below, from the extra 27 registers: profiles/r01_sweep.md)
     for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
         const int st = it & 1;
         fence_proxy_async();      // our generic-proxy accesses to the other stage precede its refill

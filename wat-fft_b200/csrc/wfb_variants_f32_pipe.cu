@@ -8,8 +8,7 @@ const std::vector<Variant> &variants_f32_pipe() {
     static const std::vector<Variant> v = {
         VP(F32_128, 16, 2, 30), VP(F32_256, 8, 2, 30), VP(F32_512, 4, 2, 31),
         VP(F32_1024, 2, 2, 33), VP(F32_1024, 1, 8, 31),
-        VP(F32_2048, 1, 4, 30), VP(F32_4096, 1, 2, 30), VP(F32_4096, 1, 3, 29), VP(F32_8192, 1, 1, 30),
-        VP(P32_4096_T128, 1, 3, 28), VP(P32_2048_T64, 1, 4, 28),
+        VP(F32_2048, 1, 4, 30), VP(F32_4096, 1, 2, 30), VP(F32_8192, 1, 1, 30),
         VP2(F32_128, 16, 2, 29), VP2(F32_256, 8, 2, 33), VP2(F32_512, 4, 2, 29), VP2(F32_512, 1, 4, 32),
     };
     return v;
