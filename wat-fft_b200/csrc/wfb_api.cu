@@ -103,7 +103,8 @@ struct wfb_plan {
     int core_n;
     size_t elem;                       // sizeof(real)
     std::vector<const Variant *> variants;
-    int variant;
+    int variant;                       // forward-direction kernel variant
+    int variant_inv;                   // inverse-direction kernel variant
     void *d_tw_fwd[8], *d_tw_inv[8];   // per variant
     void *d_rtw[8];                    // per variant (table format depends on the lane type)
     // buffers: C2C -> plane 0 / plane 1; R2C -> time / spectrum
@@ -303,6 +304,7 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
     pl->core_n = (kind == WFB_R2C) ? n / 2 : n;
     pl->elem = precision == WFB_F64 ? 8 : 4;
     pl->variant = 0;
+    pl->variant_inv = 0;
     std::vector<const std::vector<Variant> *> families;
     if (precision == WFB_F64) families = {&variants_f64_pipe(), &variants_f64()};
     else families = {&variants_f32_tile(), &variants_f32_pipe(), &variants_f32_real_pipe(), &variants_f32_x2(), &variants_f32_direct()};
@@ -312,6 +314,8 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
     std::stable_sort(pl->variants.begin(), pl->variants.end(),
                      [](const Variant *a, const Variant *b) { return a->priority > b->priority; });
     if (pl->variants.size() > 8) pl->variants.resize(8);
+    for (size_t i = 0; i < pl->variants.size(); i++)
+        if (pl->variants[i]->priority_inv > pl->variants[pl->variant_inv]->priority_inv) pl->variant_inv = (int)i;
     if (pl->variants.empty()) { *err = WFB_ERR_BAD_SIZE; delete pl; return nullptr; }
     *err = plan_init(pl);
     if (*err) { wfb_plan_destroy(pl); return nullptr; }
@@ -351,6 +355,7 @@ int wfb_plan_variant_count(wfb_plan *pl) { return pl ? (int)pl->variants.size() 
 int wfb_plan_set_variant(wfb_plan *pl, int v) {
     if (!pl || v < 0 || v >= (int)pl->variants.size()) return WFB_ERR_BAD_ARG;
     pl->variant = v;
+    pl->variant_inv = v;
     return WFB_OK;
 }
 const char *wfb_plan_variant_name(wfb_plan *pl, int v) {
@@ -368,11 +373,12 @@ unsigned long long wfb_kernel_launch_count(void) { return g_launches.load(); }
 // launches the current variant over `rows` rows starting at the given plane pointers
 static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void *in1, void *out0, void *out1,
                        long rows, cudaStream_t s) {
-    const Variant &v = *pl->variants[pl->variant];
+    const int vi = direction == WFB_INVERSE ? pl->variant_inv : pl->variant;
+    const Variant &v = *pl->variants[vi];
     KParams p;
     p.in0 = in0; p.in1 = in1; p.out0 = out0; p.out1 = out1;
-    p.tw = direction == WFB_INVERSE ? pl->d_tw_inv[pl->variant] : pl->d_tw_fwd[pl->variant];
-    p.rtw = pl->d_rtw[pl->variant];
+    p.tw = direction == WFB_INVERSE ? pl->d_tw_inv[vi] : pl->d_tw_fwd[vi];
+    p.rtw = pl->d_rtw[vi];
     p.batch = rows;
     p.scale = 1.0 / (double)pl->n;
     cudaError_t e;

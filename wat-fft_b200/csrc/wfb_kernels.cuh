@@ -1051,4 +1051,159 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
     }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Small-N real transforms (N <= 128, core M = N/2 <= 64): thread-per-row tile kernels, the real
+// counterparts of k_c2c_tile.  The Hermitian post/pre-process happens entirely in registers (the
+// thread owns every Z[k] of its row).  Spectrum rows are (M+1) complex values = an ODD number of
+// 8-byte words, so the dense [rows][M+1] tile is already bank-conflict-free for per-thread row
+// access and is copied to/from global memory as one contiguous, 16-byte aligned block.
+// ----------------------------------------------------------------------------------------
+template <class PL, int P> __host__ __device__ constexpr int slot_of_elem(int e) {
+    for (int q = 0; q < PL::E; q++) if (out_elem<PL, P>(q) == e) return q;
+    return -1;
+}
+
+template <class PL, int X, int MINB>
+__global__ void __launch_bounds__(X, MINB) k_r2c_tile(KParams p) {
+    static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 2 == 0, "tile kernel: one thread per row");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using R = float;
+    constexpr int M = PL::N, N = 2 * M;
+    constexpr int RSI = N + 4;                         // input row stride (floats): N*4 + 16 bytes
+    float *smf = reinterpret_cast<float *>(smem_raw);
+    float2 *smc = reinterpret_cast<float2 *>(smem_raw);
+    const int t = threadIdx.x;
+    const long row0 = (long)blockIdx.x * X;
+    const int rows = (p.batch - row0 < X) ? (int)(p.batch - row0) : X;
+    const float2 *tw = reinterpret_cast<const float2 *>(p.tw);
+    const float2 *rtw = reinterpret_cast<const float2 *>(p.rtw);
+
+    {   // stage in: dense [rows][N] reals -> padded rows
+        constexpr int CPR = N / 4;
+        const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.in0) + row0 * N);
+#pragma unroll
+        for (int f = t; f < X * CPR; f += X) {
+            const int r = f / CPR, c = f % CPR;
+            if (r < rows) *reinterpret_cast<float4 *>(smf + r * RSI + 4 * c) = ld_stream(src + f);
+        }
+    }
+    __syncthreads();
+
+    cx<R> x[M];
+    {
+        const float4 *rowp = reinterpret_cast<const float4 *>(smf + t * RSI);
+        static_for<M / 2>([&](auto H_) {
+            CIDX(h, H_);
+            const float4 v = rowp[h];
+            x[2 * h] = mk<R>(v.x, v.y);                // z[j] = x[2j] + i x[2j+1]
+            x[2 * h + 1] = mk<R>(v.z, v.w);
+        });
+    }
+    run_pass<R, PL, 0, false>(x, tw, 0);
+    __syncthreads();                                   // input rows and output rows alias
+
+    {   // Hermitian post-process in registers -> dense output row t ((M+1) float2, odd stride)
+        float2 *orow = smc + (size_t)t * (M + 1);
+        constexpr int HALF = M / 2;
+        const cx<R> z0 = x[slot_of_elem<PL, 0>(0)];
+        orow[0] = make_float2(z0.x + z0.y, 0.0f);
+        orow[M] = make_float2(z0.x - z0.y, 0.0f);
+        const cx<R> zh = x[slot_of_elem<PL, 0>(HALF)];
+        const cx<R> xh = RealPost<R>::middle(zh, ld_tw(rtw + HALF), M);
+        orow[HALF] = make_float2(xh.x, xh.y);
+        static_for<HALF - 1>([&](auto K_) {
+            CIDX(k0, K_);
+            constexpr int k = k0 + 1;
+            const cx<R> z = x[slot_of_elem<PL, 0>(k)], zm = x[slot_of_elem<PL, 0>(M - k)];
+            cx<R> xk, xm;
+            const twd<R> w = ld_tw(rtw + k);
+            RealPost<R>::pair(z, zm, w, w, xk, xm);
+            orow[k] = make_float2(xk.x, xk.y);
+            orow[M - k] = make_float2(xm.x, xm.y);
+        });
+    }
+    __syncthreads();
+
+    {   // stage out: rows*(M+1) float2, contiguous and 16-byte aligned (X even)
+        float2 *dst = reinterpret_cast<float2 *>(p.out0) + row0 * (M + 1);
+        const int count = rows * (M + 1);
+        const int pairs = count / 2;
+        for (int f = t; f < pairs; f += X)
+            st_stream(reinterpret_cast<float4 *>(dst) + f, reinterpret_cast<const float4 *>(smc)[f]);
+        if ((count & 1) && t == 0) st_stream(dst + (count - 1), smc[count - 1]);
+    }
+}
+
+template <class PL, int X, int MINB>
+__global__ void __launch_bounds__(X, MINB) k_c2r_tile(KParams p) {
+    static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 2 == 0, "tile kernel: one thread per row");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using R = float;
+    constexpr int M = PL::N, N = 2 * M;
+    constexpr int RSO = N + 4;                         // output row stride (floats)
+    float *smf = reinterpret_cast<float *>(smem_raw);
+    float2 *smc = reinterpret_cast<float2 *>(smem_raw);
+    const int t = threadIdx.x;
+    const long row0 = (long)blockIdx.x * X;
+    const int rows = (p.batch - row0 < X) ? (int)(p.batch - row0) : X;
+    const float2 *tw = reinterpret_cast<const float2 *>(p.tw);
+    const float2 *rtw = reinterpret_cast<const float2 *>(p.rtw);
+
+    {   // stage in: dense [rows][M+1] float2 block
+        const float2 *src = reinterpret_cast<const float2 *>(p.in0) + row0 * (M + 1);
+        const int count = rows * (M + 1);
+        const int pairs = count / 2;
+        for (int f = t; f < pairs; f += X)
+            reinterpret_cast<float4 *>(smc)[f] = ld_stream(reinterpret_cast<const float4 *>(src) + f);
+        if ((count & 1) && t == 0) smc[count - 1] = ld_stream(src + (count - 1));
+    }
+    __syncthreads();
+
+    cx<R> x[M];
+    {   // Hermitian pre-process in registers (scale 0.5/M folded in, :1674)
+        const float2 *irow = smc + (size_t)t * (M + 1);
+        constexpr int HALF = M / 2;
+        const float sc = 0.5f / float(M);
+        const float2 a0 = irow[0], am = irow[M];       // real parts only (:1679-1684)
+        x[0] = mk<R>((a0.x + am.x) * sc, (a0.x - am.x) * sc);
+        static_for<HALF>([&](auto K_) {
+            CIDX(k0, K_);
+            constexpr int k = k0 + 1;                  // 1 .. M/2 (k = M/2 is self-paired)
+            const float2 a = irow[k], b = irow[M - k];
+            const twd<R> w = ld_tw(rtw + k);
+            const float gr = a.x + b.x, gi = a.y - b.y, ur = a.x - b.x, ui = a.y + b.y;
+            const float hr = fmaf(w.y, ui, w.x * ur), hi = fmaf(w.ny, ur, w.x * ui);
+            // forward form first, mirrored second: at k = M/2 the mirrored form survives (:1722-1740)
+            x[k] = mk<R>(sc * (gr - hi), sc * (gi + hr));
+            x[M - k] = mk<R>(sc * (gr + hi), sc * (hr - gi));
+        });
+    }
+    run_pass<R, PL, 0, true>(x, tw, 0);
+    __syncthreads();                                   // input rows and output rows alias
+
+    {   // time-domain row: z[j] = (x[2j], x[2j+1]); adjacent complex pairs as one STS.128
+        float4 *rowp = reinterpret_cast<float4 *>(smf + t * RSO);
+        static_for<M>([&](auto S_) {
+            CIDX(sa, S_);
+            constexpr int ea = out_elem<PL, 0>(sa);
+            if constexpr (ea % 2 == 0) {
+                constexpr int sb = slot_of_elem<PL, 0>(ea + 1);
+                rowp[ea / 2] = make_float4(x[sa].x, x[sa].y, x[sb].x, x[sb].y);
+            }
+        });
+    }
+    __syncthreads();
+
+    {   // stage out: dense [rows][N] reals
+        constexpr int CPR = N / 4;
+        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out0) + row0 * N);
+#pragma unroll
+        for (int f = t; f < X * CPR; f += X) {
+            const int r = f / CPR, c = f % CPR;
+            if (r < rows) st_stream(dst + f, *reinterpret_cast<const float4 *>(smf + r * RSO + 4 * c));
+        }
+    }
+}
+
 }  // namespace wfb

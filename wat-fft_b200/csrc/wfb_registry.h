@@ -20,6 +20,7 @@ struct Variant {
     size_t smem;       // dynamic shared memory per CTA
     int lanes;         // batch rows per thread group: 2 for the packed-FP32 (f32x2) kernels
     int priority;      // larger = preferred default (set from measurements, profiles/)
+    int priority_inv;  // same for the inverse direction (c2r / ifft); -1 = same as `priority`
     std::vector<int> radices;
     launch_fn c2c, r2c, c2r;
 };
@@ -68,8 +69,8 @@ template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
         return launch_grid((const void *)k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, ctas(batch), p, s);
     }
-    static Variant make(const char *name, int priority) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, plan_radices<PL>(), &c2c, &r2c, &c2r};
+    static Variant make(const char *name, int priority, int priority_inv = -1) {
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), &c2c, &r2c, &c2r};
     }
 };
 
@@ -86,8 +87,8 @@ template <typename R, class PL, int X, int MINB> struct PipeLaunchers {
             k = dir ? (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB>;
         return launch_persistent(k, smem, PL::T * X, tiles(batch), p, s);
     }
-    static Variant make(const char *name, int priority) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    static Variant make(const char *name, int priority, int priority_inv = -1) {
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), &c2c, nullptr, nullptr};
     }
 };
 
@@ -101,8 +102,8 @@ template <typename R, class PL, int X, int MINB> struct RealPipeLaunchers {
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
         return launch_persistent((const void *)k_real_pipe<R, PL, X, PADQ, true, MINB>, smem_i, PL::T * X, (batch + X - 1) / X, p, s);
     }
-    static Variant make(const char *name, int priority) {
-        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, plan_radices<PL>(), nullptr, &r2c, &c2r};
+    static Variant make(const char *name, int priority, int priority_inv = -1) {
+        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 
@@ -117,8 +118,22 @@ template <class PL, int X, int MINB> struct TileLaunchers {
             k = dir ? (const void *)k_c2c_tile<float, PL, X, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_tile<float, PL, X, IO_INTERLEAVED, false, MINB>;
         return launch_grid(k, smem, X, (batch + X - 1) / X, p, s);
     }
-    static Variant make(const char *name, int priority) {
-        return Variant{name, PL::N, X, X, smem, 1, priority, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    static Variant make(const char *name, int priority, int priority_inv = -1) {
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    }
+};
+
+// thread-per-row tile kernels for the real transforms (core M <= 64)
+template <class PL, int X, int MINB> struct RealTileLaunchers {
+    static constexpr size_t smem = sizeof(float) * (size_t)(2 * PL::N + 4) * X;
+    static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_grid((const void *)k_r2c_tile<PL, X, MINB>, smem, X, (batch + X - 1) / X, p, s);
+    }
+    static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_grid((const void *)k_c2r_tile<PL, X, MINB>, smem, X, (batch + X - 1) / X, p, s);
+    }
+    static Variant make(const char *name, int priority, int priority_inv = -1) {
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 

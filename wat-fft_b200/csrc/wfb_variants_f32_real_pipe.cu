@@ -1,11 +1,11 @@
 // persistent TMA-pipelined r2c / c2r f32 kernels (core size M = N/2)
 #include "wfb_registry.h"
 namespace wfb {
-#define VR(PL, X, MINB, PRIO) RealPipeLaunchers<float, PL, X, MINB>::make(#PL "_rpipe" #X, PRIO)
+#define VR(PL, X, MINB, ...) RealPipeLaunchers<float, PL, X, MINB>::make(#PL "_rpipe" #X, __VA_ARGS__)
 const std::vector<Variant> &variants_f32_real_pipe() {
     static const std::vector<Variant> v = {
-        VR(F32_64, 32, 2, 30), VR(F32_128, 16, 2, 30), VR(F32_256, 8, 2, 30), VR(F32_512, 4, 2, 30),
-        VR(F32_1024, 2, 2, 30), VR(F32_2048, 2, 2, 30), VR(F32_4096, 2, 1, 30),
+        VR(F32_64, 32, 2, 30), VR(F32_128, 16, 2, 9, 30), VR(F32_256, 8, 2, 30), VR(F32_512, 4, 2, 30),
+        VR(F32_1024, 2, 2, 30), VR(F32_2048, 2, 2, 30, 9), VR(F32_4096, 2, 1, 30),
     };
     return v;
 }

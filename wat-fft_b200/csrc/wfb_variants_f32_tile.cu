@@ -2,9 +2,11 @@
 #include "wfb_registry.h"
 namespace wfb {
 #define V(PL, X, MINB, PRIO) TileLaunchers<PL, X, MINB>::make(#PL "_tile", PRIO)
+#define VR(PL, X, MINB, PRIO) RealTileLaunchers<PL, X, MINB>::make(#PL "_rtile", PRIO)
 const std::vector<Variant> &variants_f32_tile() {
     static const std::vector<Variant> v = {
         V(F32_4, 256, 2, 50), V(F32_8, 256, 2, 50), V(F32_16, 256, 2, 50), V(T32_32, 128, 2, 50), V(T32_64, 128, 1, 50),
+        VR(F32_16, 256, 2, 50), VR(T32_32, 128, 2, 50), VR(T32_64, 128, 1, 25),
     };
     return v;
 }
