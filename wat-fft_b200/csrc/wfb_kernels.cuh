@@ -777,7 +777,7 @@ template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr s
     return (a + 127) / 128 * 128;
 }
 
-template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB>
+template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, bool RC = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -786,7 +786,12 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
     constexpr int LANES = RT<R>::LANES;
     constexpr int N = PL::N;
     constexpr int LAST = PL::npass() - 1;
-    constexpr int ROWS = X * LANES;                 // rows per CTA iteration (one dense tile)
+    constexpr int ROWS = X * LANES;                 // rows per CTA iteration
+    // RC ("row copies"): one bulk copy per row into rows padded by N/16 elements, so that the
+    // 32/T rows a warp reads side by side start T banks apart (a dense tile puts every row on
+    // bank 0: ncu showed 4-way conflicts and mio_throttle as the top stall at N = 128)
+    constexpr int RSTR = RC ? N + N / 16 : N;       // smem row stride, elements
+    static_assert(!RC || (N >= 64 && PL::T * X >= 32), "row copies need 16-byte aligned padded rows and a full issuing warp");
     constexpr size_t BUF = pipe_buf_bytes<R, PL, PADQ, X>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
@@ -800,24 +805,37 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
     }
     __syncthreads();
 
-    auto issue = [&](long tile, int st) {       // elected thread: stream the tile's rows into stage st
+    // stream a tile's rows into stage st: thread 0 (dense tile: one copy per plane) or warp 0
+    // (row copies: one copy per row and plane, spread over the lanes)
+    auto issue = [&](long tile, int st) {
         const long row = tile * ROWS;
         const int rows = (p.batch - row < ROWS) ? (int)(p.batch - row) : ROWS;
         unsigned char *dst = smem_raw + st * BUF;
-        if constexpr (IO == IO_SPLIT) {
-            const uint32_t bytes = (uint32_t)(rows * N * sizeof(S));
-            mbar_expect_tx(mbar + st, 2 * bytes);
-            tma_load_1d(dst, reinterpret_cast<const S *>(p.in0) + row * N, bytes, mbar + st);
-            tma_load_1d(dst + ROWS * N * sizeof(S), reinterpret_cast<const S *>(p.in1) + row * N, bytes, mbar + st);
+        constexpr int PLANES = (IO == IO_SPLIT) ? 2 : 1;
+        constexpr uint32_t ROWB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * N * sizeof(S));     // bytes per row per plane
+        constexpr uint32_t RSB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * RSTR * sizeof(S));  // smem row stride, bytes
+        if constexpr (!RC) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(mbar + st, PLANES * rows * ROWB);
+                tma_load_1d(dst, reinterpret_cast<const unsigned char *>(p.in0) + row * ROWB, rows * ROWB, mbar + st);
+                if constexpr (PLANES == 2)
+                    tma_load_1d(dst + ROWS * RSB, reinterpret_cast<const unsigned char *>(p.in1) + row * ROWB, rows * ROWB, mbar + st);
+            }
         } else {
-            const uint32_t bytes = (uint32_t)(rows * N * 2 * sizeof(S));
-            mbar_expect_tx(mbar + st, bytes);
-            tma_load_1d(dst, reinterpret_cast<const S *>(p.in0) + row * 2 * N, bytes, mbar + st);
+            if (threadIdx.x < 32) {
+                if (threadIdx.x == 0) mbar_expect_tx(mbar + st, PLANES * rows * ROWB);
+                __syncwarp();
+                for (int c = threadIdx.x; c < PLANES * rows; c += 32) {
+                    const int pl = c / rows, r = c - pl * rows;
+                    const unsigned char *src = reinterpret_cast<const unsigned char *>(pl ? p.in1 : p.in0) + (row + r) * ROWB;
+                    tma_load_1d(dst + (size_t)(pl * ROWS + r) * RSB, src, ROWB, mbar + st);
+                }
+            }
         }
     };
 
     long tile = blockIdx.x;
-    if (threadIdx.x == 0 && tile < tiles) issue(tile, 0);
+    if (tile < tiles) issue(tile, 0);
     cx<R> x[PL::E];
     // (hoisting the last pass's thread-invariant twiddles into registers was tried and measured
     //  neutral at N = 4096 and 3-6 % slower below, from the extra 27 registers: profiles/r01_sweep.md)
@@ -825,7 +843,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
         const int st = it & 1;
         fence_proxy_async();      // our generic-proxy accesses to the other stage precede its refill
         __syncthreads();          // ... and everyone is done using it as scratch
-        if (threadIdx.x == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        if (tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
         mbar_wait(mbar + st, (it >> 1) & 1);
 
         const long row = tile * ROWS + (long)xi * LANES;
@@ -833,23 +851,23 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
         const bool two = LANES == 2 && row + 1 < p.batch;
         unsigned char *buf = smem_raw + st * BUF;
         if constexpr (IO == IO_SPLIT) {
-            const S *re = reinterpret_cast<const S *>(buf) + (size_t)xi * LANES * N + tid;
-            const S *im = re + ROWS * N;
+            const S *re = reinterpret_cast<const S *>(buf) + (size_t)xi * LANES * RSTR + tid;
+            const S *im = re + ROWS * RSTR;
             static_for<PL::E>([&](auto E_) {
                 CIDX(e, E_);
                 if constexpr (LANES == 2) {
-                    x[e].x.v = make_float2(re[e * PL::T], re[N + e * PL::T]);
-                    x[e].y.v = make_float2(im[e * PL::T], im[N + e * PL::T]);
+                    x[e].x.v = make_float2(re[e * PL::T], re[RSTR + e * PL::T]);
+                    x[e].y.v = make_float2(im[e * PL::T], im[RSTR + e * PL::T]);
                 } else {
                     x[e] = mk<R>(re[e * PL::T], im[e * PL::T]);
                 }
             });
         } else {
-            const V2 *z = reinterpret_cast<const V2 *>(buf) + (size_t)xi * LANES * N + tid;
+            const V2 *z = reinterpret_cast<const V2 *>(buf) + (size_t)xi * LANES * RSTR + tid;
             static_for<PL::E>([&](auto E_) {
                 CIDX(e, E_);
                 if constexpr (LANES == 2) {
-                    const V2 a = z[e * PL::T], b = z[N + e * PL::T];
+                    const V2 a = z[e * PL::T], b = z[RSTR + e * PL::T];
                     x[e].x.v = make_float2(a.x, b.x);
                     x[e].y.v = make_float2(a.y, b.y);
                 } else {
@@ -907,16 +925,18 @@ template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ c
     return (a + 127) / 128 * 128;
 }
 
-template <typename R, class PL, int X, int PADQ, bool C2R, int MINB>
+template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
     static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
     static_assert(!C2R || X % 2 == 0, "c2r tiles need an even number of rows (16-byte alignment)");
+    static_assert(!RC || (!C2R && PL::N >= 32 && PL::T * X >= 32), "row copies: r2c only (c2r rows are 8-byte aligned)");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using S = typename VecOf<R>::s;
     using V2 = typename VecOf<R>::v2;
     constexpr int M = PL::N;
     constexpr int LAST = PL::npass() - 1;
     constexpr int IN_ROW = C2R ? M + 1 : M;          // row lengths in complex values
+    constexpr int RSTR = RC ? M + M / 16 : IN_ROW;   // smem row stride (RC: rows T banks apart, see k_c2c_pipe)
     constexpr size_t BUF = real_pipe_buf_bytes<R, PL, PADQ, X, C2R>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
@@ -936,20 +956,33 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
     auto tma_ok = [&](long tile) { return !C2R || (tile_rows(tile) % 2 == 0); };
     auto issue = [&](long tile, int st) {
         if (!tma_ok(tile)) return;
-        const uint32_t bytes = (uint32_t)(tile_rows(tile) * IN_ROW * sizeof(V2));
-        mbar_expect_tx(mbar + st, bytes);
-        tma_load_1d(smem_raw + st * BUF, gin + tile * X * IN_ROW, bytes, mbar + st);
+        const int rows = tile_rows(tile);
+        if constexpr (!RC) {
+            if (threadIdx.x == 0) {
+                const uint32_t bytes = (uint32_t)(rows * IN_ROW * sizeof(V2));
+                mbar_expect_tx(mbar + st, bytes);
+                tma_load_1d(smem_raw + st * BUF, gin + tile * X * IN_ROW, bytes, mbar + st);
+            }
+        } else {
+            if (threadIdx.x < 32) {
+                if (threadIdx.x == 0) mbar_expect_tx(mbar + st, (uint32_t)(rows * IN_ROW * sizeof(V2)));
+                __syncwarp();
+                for (int r = threadIdx.x; r < rows; r += 32)
+                    tma_load_1d(smem_raw + st * BUF + (size_t)r * RSTR * sizeof(V2), gin + (tile * X + r) * IN_ROW,
+                                (uint32_t)(IN_ROW * sizeof(V2)), mbar + st);
+            }
+        }
     };
 
     long tile = blockIdx.x;
-    if (threadIdx.x == 0 && tile < tiles) issue(tile, 0);
+    if (tile < tiles) issue(tile, 0);
     cx<R> x[PL::E];
     unsigned phasebits = 0;                            // mbarrier phase parity per stage (bit st)
     for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
         const int st = it & 1;
         fence_proxy_async();
         __syncthreads();
-        if (threadIdx.x == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        if (tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
         unsigned char *buf = smem_raw + st * BUF;
         if (tma_ok(tile)) {
             mbar_wait(mbar + st, (phasebits >> st) & 1u);
@@ -963,7 +996,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
         const long row = tile * X + xi;
         const bool active = row < p.batch;
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(M);
-        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xi * IN_ROW;
+        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xi * RSTR;
 
         if constexpr (!C2R) {
             // ---------------- r2c

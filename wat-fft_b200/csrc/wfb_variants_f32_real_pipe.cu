@@ -2,9 +2,11 @@
 #include "wfb_registry.h"
 namespace wfb {
 #define VR(PL, X, MINB, ...) RealPipeLaunchers<float, PL, X, MINB>::make(#PL "_rpipe" #X, __VA_ARGS__)
+#define VRC(PL, X, MINB, ...) RealPipeLaunchers<float, PL, X, MINB, true>::make(#PL "_rpipe" #X "_rc", __VA_ARGS__)
 const std::vector<Variant> &variants_f32_real_pipe() {
     static const std::vector<Variant> v = {
         VR(F32_64, 32, 2, 30), VR(F32_128, 16, 2, 9, 30), VR(F32_256, 8, 2, 30), VR(F32_512, 4, 2, 30),
+        VRC(F32_64, 32, 2, 31, 8), VRC(F32_128, 16, 2, 31, 8), VRC(F32_256, 16, 2, 29, 8),
         VR(F32_1024, 2, 2, 30), VR(F32_2048, 2, 2, 30, 9), VR(F32_4096, 2, 1, 30),
     };
     return v;
