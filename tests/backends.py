@@ -35,7 +35,18 @@ class OracleBackend(_Loop):
 
 
 class WatRefBackend(_Loop):
+    """rfft_split needs n >= 32; below that the public f32 real context is backed by fft_real_f32_dual."""
     name = "watref"
+
+    def rfft_f32(self, x):
+        if x.shape[-1] < 32:
+            return np.stack([self.impl.rfft_f32_dual(r) for r in x])
+        return super().rfft_f32(x)
+
+    def irfft_f32(self, s):
+        if s.shape[-1] - 2 < 32:
+            return np.stack([self.impl.irfft_f32_dual(r) for r in s])
+        return super().irfft_f32(s)
 
 
 class GpuBackend:

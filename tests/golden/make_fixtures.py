@@ -43,6 +43,11 @@ def main():
             out[f"irfft32_{n}"] = w.irfft_split_f32(spec)
         if n >= 8:
             out[f"rfft64_{n}"] = w.rfft_f64(xr)
+        if 8 <= n <= 256:
+            # the module behind the public createRFFTf32 context (fft_real_f32_dual): pins N = 8, 16
+            spec = w.rfft_f32_dual(xr.astype(np.float32))
+            out[f"rfft32dual_{n}"] = spec
+            out[f"irfft32dual_{n}"] = w.irfft_f32_dual(spec)
     path = Path(__file__).resolve().parent / "watref_vectors.npz"
     np.savez_compressed(path, **out)
     print(f"wrote {path} ({path.stat().st_size} bytes, {len(out)} arrays)")

@@ -40,7 +40,7 @@ def test_size_ranges(wf):
     lo, hi = ctypes.c_int(), ctypes.c_int()
     assert lib.wfb_size_range(C.C2C, C.F32, C.SPLIT, lo, hi) == 0 and (lo.value, hi.value) == (4, 8192)
     assert lib.wfb_size_range(C.C2C, C.F32, C.INTERLEAVED, lo, hi) == 0 and (lo.value, hi.value) == (4, 8192)
-    assert lib.wfb_size_range(C.R2C, C.F32, 0, lo, hi) == 0 and (lo.value, hi.value) == (32, 16384)
+    assert lib.wfb_size_range(C.R2C, C.F32, 0, lo, hi) == 0 and (lo.value, hi.value) == (8, 16384)
     assert lib.wfb_size_range(C.C2C, C.F64, C.INTERLEAVED, lo, hi) == 0
     assert lib.wfb_size_range(C.C2C, C.F64, C.SPLIT, lo, hi) == C.ERR_UNSUPPORTED
     assert lib.wfb_size_range(7, C.F32, 0, lo, hi) == C.ERR_UNSUPPORTED
@@ -60,7 +60,7 @@ def test_plan_validation_order(wf):
             wf.Plan(C.C2C, C.F32, C.SPLIT, n)
         assert e.value.code == C.ERR_BAD_SIZE
     with pytest.raises(wf.WatFFTError) as e:
-        wf.Plan(C.R2C, C.F32, 0, 16)          # rfft_split needs n >= 32
+        wf.Plan(C.R2C, C.F32, 0, 4)           # real f32 contexts start at n = 8
     assert e.value.code == C.ERR_BAD_SIZE
     with pytest.raises(wf.WatFFTError) as e:
         wf.Plan(C.C2C, C.F32, C.SPLIT, 64, batch=0)

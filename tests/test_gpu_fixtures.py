@@ -55,6 +55,16 @@ def test_gpu_vs_reference_module_fixtures(wf, n):
         c.forward()
         assert rel_err(c.getOutputBuffer(), FIX[f"rfft64_{n}"], xr) <= f64_bound(n)
         c.dispose()
+    if 8 <= n <= 256:
+        # createRFFTf32 against the module that backs it in the reference (fft_real_f32_dual), N >= 8
+        c = wf.createRFFTf32(n)
+        c.getInputBuffer()[:] = xr.astype(np.float32)
+        c.forward()
+        assert rel_err(c.getOutputBuffer(), FIX[f"rfft32dual_{n}"], xr) <= f32_bound(n)
+        c.getOutputBuffer()[:] = FIX[f"rfft32dual_{n}"]
+        c.inverse()
+        assert rel_err(c.getInputBuffer(), FIX[f"irfft32dual_{n}"], FIX[f"rfft32dual_{n}"]) <= f32_bound(n)
+        c.dispose()
 
 
 @pytest.mark.parametrize("n", [16, 256, 4096])
@@ -170,3 +180,46 @@ def test_exports_facade(wf):
     ex.ifft_split(n)
     assert np.max(np.abs(re - a)) < 1e-4
     ex.dispose()
+
+
+def test_staged_pipeline_large_batch(wf, oracle):
+    """wfb_exec with host buffers switches to the chunked multi-stream H2D/kernel/D2H pipeline for
+    large batches; rows from every chunk (first, interior, last, ragged tail) must still be right."""
+    n = 1024
+    batch = 65536 + 3                       # 256 MiB per plane -> several 32 MiB chunks + ragged tail
+    rng = np.random.default_rng(11)
+    ctx = wf.createFFTf32Split(n, batch=batch)
+    re, im = ctx.getRealBuffer().reshape(batch, n), ctx.getImagBuffer().reshape(batch, n)
+    rows = [0, 1, 8191, 8192, 8193, 30000, batch - 4, batch - 1]
+    src = {}
+    re[:] = 0.0
+    im[:] = 0.0
+    for r in rows:
+        src[r] = (rng.uniform(-1, 1, n).astype(np.float32), rng.uniform(-1, 1, n).astype(np.float32))
+        re[r], im[r] = src[r]
+    ctx.forward()
+    for r in rows:
+        er, ei = oracle.fft_split_f32(*src[r])
+        assert rel_err(np.r_[re[r], im[r]], np.r_[er, ei], np.r_[src[r][0], src[r][1]]) <= f32_bound(n), r
+    assert not re[2].any() and not im[40000].any()          # untouched rows stay zero
+    ctx.inverse()
+    for r in rows:
+        assert np.max(np.abs(re[r] - src[r][0])) < 1e-4 and np.max(np.abs(im[r] - src[r][1])) < 1e-4
+    ctx.dispose()
+    # real transform: different input / output row strides through the same pipeline
+    n = 4096
+    batch = 20000 + 1
+    rc = wf.createRFFTf32(n, batch=batch)
+    t, s = rc.getInputBuffer().reshape(batch, n), rc.getOutputBuffer().reshape(batch, n + 2)
+    t[:] = 0.0
+    rows = [0, 2047, 2048, 9999, batch - 1]
+    xs = {r: rng.uniform(-1, 1, n).astype(np.float32) for r in rows}
+    for r in rows:
+        t[r] = xs[r]
+    rc.forward()
+    for r in rows:
+        assert rel_err(s[r], oracle.rfft_split_f32(xs[r]), xs[r]) <= f32_bound(n), r
+    rc.inverse()
+    for r in rows:
+        assert np.max(np.abs(t[r] - xs[r])) < 1e-4
+    rc.dispose()

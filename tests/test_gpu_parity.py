@@ -10,7 +10,7 @@ from conftest import f32_bound, f64_bound, rel_err
 pytestmark = pytest.mark.gpu
 
 C2C_SIZES = [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
-R2C_F32_SIZES = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
+R2C_F32_SIZES = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
 R2C_F64_SIZES = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
 
 

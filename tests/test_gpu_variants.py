@@ -48,7 +48,7 @@ def test_c2c_f32_all_variants(wf, oracle, n):
         plan.destroy()
 
 
-@pytest.mark.parametrize("n", [32, 64, 128, 256, 1024, 4096, 16384])
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 1024, 4096, 16384])
 def test_real_f32_all_variants(wf, oracle, n):
     C = wf._cabi
     b = _batch(n)

@@ -74,6 +74,14 @@ def test_oracle_vs_committed_fixtures(oracle, n):
         assert np.array_equal(oracle.irfft_split_f32(FIX[f"rfft32_{n}"]), FIX[f"irfft32_{n}"])
     if n >= 8:
         assert np.max(np.abs(oracle.rfft_f64(xr) - FIX[f"rfft64_{n}"])) <= 8e-16 * np.linalg.norm(xr)
+    if 8 <= n <= 256:
+        # rfft_split's algorithm (the restatement, any n >= 8) against the OTHER f32 real module of the
+        # reference (fft_real_f32_dual, which backs createRFFTf32): different algorithm, f32 tolerance
+        x32 = xr.astype(np.float32)
+        s = oracle.rfft_split_f32(x32)
+        assert np.max(np.abs(s - FIX[f"rfft32dual_{n}"])) <= 2e-6 * np.log2(n) * np.linalg.norm(x32)
+        back = oracle.irfft_split_f32(FIX[f"rfft32dual_{n}"])
+        assert np.max(np.abs(back - FIX[f"irfft32dual_{n}"])) <= 2e-6 * np.log2(n) * np.linalg.norm(FIX[f"rfft32dual_{n}"])
 
 
 def test_lcg_matches_js_double_rounding():

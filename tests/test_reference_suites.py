@@ -156,7 +156,7 @@ def test_per_bin_f32_complex(be, n):
         assert np.max(np.abs(ilo[k] - exp)) < tol, ("interleaved", n, k)
 
 
-@pytest.mark.parametrize("n", [32, 64, 128, 256])
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256])      # 8, 16: the fft_real_f32_dual sizes (:179-229)
 def test_per_bin_f32_real(be, n):
     t = np.arange(n)
     bins = np.arange(n // 2 + 1)

@@ -169,7 +169,10 @@ int wfb_size_range(int kind, int precision, int layout, int *min_n, int *max_n) 
         else if (precision == WFB_F64 && layout == WFB_INTERLEAVED) { lo = 4; hi = 8192; }
         else return WFB_ERR_UNSUPPORTED;
     } else if (kind == WFB_R2C) {
-        if (precision == WFB_F32) { lo = 32; hi = 16384; }     // rfft_split requires n >= 32 (fft_split_native_f32.wat:1562)
+        // rfft_split itself requires n >= 32 (fft_split_native_f32.wat:1562); n = 8 and 16 are accepted because
+        // the public createRFFTf32 context does (it is backed by fft_real_f32_dual, benchmarks/shared/
+        // wat-surfaces.mjs:133-141): same I/O contract, tolerance-based parity against that module
+        if (precision == WFB_F32) { lo = 8; hi = 16384; }
         else if (precision == WFB_F64) { lo = 8; hi = 16384; }
         else return WFB_ERR_UNSUPPORTED;
     } else return WFB_ERR_UNSUPPORTED;
