@@ -134,6 +134,33 @@ WFB_API unsigned long long wfb_kernel_launch_count(void);
  * 1 = f32 interleaved module, 2 = f64 modules.  re/im are float* for 0/1, double* for 2. */
 WFB_API int wfb_reference_twiddles(int flavour, int n, int count, void *re, void *im);
 
+/* ---- batched STFT front-end (the reference's batched caller) ------------------------------
+ * Replaces the per-frame JavaScript loop of playground/src/spectrogram.js:281-360
+ * (slice -> applyWindow :27-38 -> zeroPad :40-45 -> context.run() -> computeMagnitude :47-58 ->
+ * magnitudeToDb :60-62 -> gain/range normalisation :335-352) by ONE kernel launch over all frames:
+ * frame gather, window multiply and zero padding are fused into the r2c load stage, |X| -> dB ->
+ * [0,1] into its store stage.
+ *   frames = floor((num_samples - window) / hop) + 1,  window = fft_size / zero_padding,
+ *   bins   = fft_size/2 + 1.
+ * Output, mode WFB_STFT_DB: float [frames][bins] in [0,1] (bins 0..2 forced to 0, :338-342);
+ *         mode WFB_STFT_COMPLEX: float [frames][bins][2] (the raw spectra of the windowed frames). */
+typedef struct wfb_stft wfb_stft;
+enum { WFB_WINDOW_HANN = 0, WFB_WINDOW_HAMMING = 1, WFB_WINDOW_BLACKMAN = 2, WFB_WINDOW_BLACKMAN_HARRIS = 3,
+       WFB_WINDOW_RECTANGULAR = 4 };
+enum { WFB_STFT_DB = 0, WFB_STFT_COMPLEX = 1 };
+WFB_API wfb_stft *wfb_stft_create(int fft_size, int zero_padding, int hop, int window_type, long num_samples,
+                                  int mode, float gain_db, float range_db, int device, int flags, int *err);
+WFB_API void wfb_stft_destroy(wfb_stft *st);
+WFB_API long wfb_stft_frames(wfb_stft *st);
+WFB_API int wfb_stft_bins(wfb_stft *st);
+WFB_API void *wfb_stft_host_samples(wfb_stft *st);      /* pinned, num_samples floats */
+WFB_API void *wfb_stft_host_output(wfb_stft *st);       /* pinned, wfb_stft_output_bytes() */
+WFB_API size_t wfb_stft_output_bytes(wfb_stft *st);
+WFB_API int wfb_stft_exec(wfb_stft *st, int flags);     /* flags as wfb_exec */
+WFB_API int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void *stream);
+/* Algorithmic bytes of one exec: every sample read once + the output written once. */
+WFB_API size_t wfb_stft_algorithmic_bytes(wfb_stft *st);
+
 #ifdef __cplusplus
 }
 #endif

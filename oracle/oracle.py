@@ -327,3 +327,52 @@ def dft(z, inverse=False):
 def real_dft(x):
     x = np.asarray(x, np.float64)
     return dft(x.astype(np.complex128))[: x.size // 2 + 1]
+
+
+# ----------------------------------------------------------------------
+# STFT / spectrogram front-end: playground/src/spectrogram.js restated
+# ----------------------------------------------------------------------
+def window_function(window_type: str, n: int) -> np.ndarray:
+    """WINDOW_FUNCTIONS, spectrogram.js:1-25 (evaluated in double, like the JS)."""
+    i = np.arange(n, dtype=np.float64)
+    x = 2 * np.pi * i / (n - 1)
+    if window_type == "hamming":
+        return 0.54 - 0.46 * np.cos(x)
+    if window_type == "blackman":
+        return 0.42 - 0.5 * np.cos(x) + 0.08 * np.cos(2 * x)
+    if window_type == "blackmanHarris":
+        return 0.35875 - 0.48829 * np.cos(x) + 0.14128 * np.cos(2 * x) - 0.01168 * np.cos(3 * x)
+    if window_type == "rectangular":
+        return np.ones(n)
+    return 0.5 * (1 - np.cos(x))          # hann, also the fallback for unknown names (:31)
+
+
+def spectrogram_reference(samples, fft_size, hop, window_type="hann", zero_padding=1, gain=0.0, range_db=80.0,
+                          rfft=None, complex_out=False):
+    """generateSpectrogram, spectrogram.js:281-360: per frame slice -> applyWindow (:27-38, product
+    rounded to f32) -> zeroPad (:40-45) -> real FFT -> computeMagnitude (:47-58, rounded to f32) ->
+    magnitudeToDb (:60-62) -> gain/range normalisation with the first 3 bins zeroed (:335-352).
+    `rfft` is the f32 real transform (n reals -> n+2 interleaved floats)."""
+    samples = np.asarray(samples, np.float32)
+    wsize = fft_size // zero_padding
+    bins = fft_size // 2 + 1
+    frames = (len(samples) - wsize) // hop + 1
+    if frames <= 0:
+        raise ValueError("Audio too short for the given FFT size")
+    w = window_function(window_type, wsize)
+    out = np.zeros((frames, bins, 2) if complex_out else (frames, bins), np.float32)
+    for f in range(frames):
+        frame = samples[f * hop: f * hop + wsize]
+        padded = np.zeros(fft_size, np.float32)
+        padded[:wsize] = (frame.astype(np.float64) * w).astype(np.float32)
+        spec = np.asarray(rfft(padded), np.float32)
+        re, im = spec[0::2].astype(np.float64), spec[1::2].astype(np.float64)
+        if complex_out:
+            out[f, :, 0], out[f, :, 1] = re, im
+            continue
+        mag = np.sqrt(re * re + im * im).astype(np.float32).astype(np.float64)
+        db = 20 * np.log10(mag / (fft_size / 2) + 1e-10)
+        norm = np.clip((db - (gain - range_db)) / range_db, 0.0, 1.0)
+        norm[:3] = 0.0
+        out[f] = norm
+    return out

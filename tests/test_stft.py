@@ -1,0 +1,88 @@
+"""Batched STFT front-end: the reference's spectrogram loop
+(playground/src/spectrogram.js:281-360) restated in oracle/oracle.py and fused into one kernel."""
+import numpy as np
+import pytest
+
+import oracle as om
+from conftest import f32_bound
+
+
+def _signal(n, rate=16000.0, seed=0):
+    t = np.arange(n) / rate
+    rng = np.random.default_rng(seed)
+    chirp = np.sin(2 * np.pi * (200 + 1500 * t) * t)
+    return (0.6 * chirp + 0.3 * np.sin(2 * np.pi * 3000 * t) + 0.05 * rng.uniform(-1, 1, n)).astype(np.float32)
+
+
+# ------------------------------------------------------------------ CPU: the restatement itself
+def test_window_functions():
+    for name in ("hann", "hamming", "blackman", "blackmanHarris", "rectangular", "nonsense"):
+        w = om.window_function(name, 64)
+        assert w.shape == (64,) and np.all(w <= 1.0 + 1e-12)
+        assert np.allclose(w, w[::-1])                       # all symmetric
+    assert om.window_function("hann", 8)[0] == 0.0 and abs(om.window_function("hamming", 8)[0] - 0.08) < 1e-12
+    assert np.array_equal(om.window_function("nonsense", 16), om.window_function("hann", 16))
+
+
+def test_reference_spectrogram_tone(oracle, watref):
+    rate, n_fft, hop = 16000.0, 256, 64
+    t = np.arange(4096) / rate
+    x = np.sin(2 * np.pi * 2000.0 * t).astype(np.float32)
+    s = om.spectrogram_reference(x, n_fft, hop, "hann", rfft=oracle.rfft_split_f32)
+    assert s.shape == ((4096 - 256) // 64 + 1, 129) and s.dtype == np.float32
+    assert np.all(s[:, :3] == 0.0) and s.min() >= 0.0 and s.max() <= 1.0
+    assert np.all(np.argmax(s, axis=1) == round(2000.0 / rate * n_fft))       # bin 32
+    # the same loop over the reference's own module gives the same picture
+    s2 = om.spectrogram_reference(x, n_fft, hop, "hann", rfft=watref.rfft_split_f32)
+    assert np.max(np.abs(s - s2)) < 1e-5
+    with pytest.raises(ValueError):
+        om.spectrogram_reference(x[:100], n_fft, hop, rfft=oracle.rfft_split_f32)
+
+
+# ------------------------------------------------------------------ GPU parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_fft,hop,window,zp", [(64, 16, "hann", 1), (256, 64, "hamming", 1), (1024, 100, "blackman", 1),
+                                                 (1024, 256, "hann", 2), (4096, 1024, "blackmanHarris", 4),
+                                                 (8192, 2048, "rectangular", 1), (512, 37, "hann", 1)])
+def test_gpu_spectrogram_matches_reference_loop(wf, oracle, n_fft, hop, window, zp):
+    x = _signal(3 * n_fft + 5 * hop + 11, seed=n_fft)
+    ref = om.spectrogram_reference(x, n_fft, hop, window, zp, gain=-6.0, range_db=70.0, rfft=oracle.rfft_split_f32)
+    got = wf.generateSpectrogram(x, 16000.0, n_fft, hop, window, zp, gain=-6.0, range=70.0)
+    assert got["numFrames"] == ref.shape[0] and got["numBins"] == ref.shape[1] == n_fft // 2 + 1
+    assert got["windowSize"] == n_fft // zp and got["fftSize"] == n_fft and got["hopSize"] == hop
+    g = got["data"].reshape(ref.shape)
+    assert np.all(g[:, :3] == 0.0)
+    # normalised dB in [0,1]: f32 rounding of |X| moves a value by ~1e-6; bins at the clip edges by a bit more
+    assert np.max(np.abs(g - ref)) < 2e-4, np.max(np.abs(g - ref))
+    # raw spectra of the windowed frames, against the oracle's r2c of the same frames
+    sp = wf.Spectrogram(len(x), n_fft, hop, window, zp, mode="complex")
+    sp.getInputBuffer()[:] = x
+    sp.run()
+    gc = sp.getOutputBuffer().copy()
+    sp.dispose()
+    rc = om.spectrogram_reference(x, n_fft, hop, window, zp, rfft=oracle.rfft_split_f32, complex_out=True)
+    wsize = n_fft // zp
+    w = om.window_function(window, wsize)
+    for f in sorted({0, ref.shape[0] // 2, ref.shape[0] - 1}):
+        frame = (x[f * hop: f * hop + wsize].astype(np.float64) * w).astype(np.float32)
+        err = np.max(np.abs(gc[f].astype(np.float64) - rc[f])) / np.linalg.norm(frame)
+        assert err <= f32_bound(n_fft), (f, err)
+
+
+@pytest.mark.gpu
+def test_gpu_spectrogram_errors_and_long_signal(wf, oracle):
+    with pytest.raises(ValueError):
+        wf.generateSpectrogram(np.zeros(100, np.float32), 16000.0, 1024, 256)
+    with pytest.raises(wf.WatFFTError):
+        wf.Spectrogram(100000, 1000, 256)                    # not a power of two
+    with pytest.raises(wf.WatFFTError):
+        wf.Spectrogram(100000, 32, 8)                        # below the supported FFT sizes
+    # one launch over ~15k frames; spot-check frames against the loop
+    x = _signal(1 << 20, seed=3)
+    got = wf.generateSpectrogram(x, 16000.0, 1024, 64)
+    frames = got["numFrames"]
+    assert frames == ((1 << 20) - 1024) // 64 + 1
+    g = got["data"].reshape(frames, 513)
+    for f in (0, 1, frames // 2, frames - 1):
+        ref = om.spectrogram_reference(x[f * 64: f * 64 + 1024], 1024, 64, rfft=oracle.rfft_split_f32)
+        assert np.max(np.abs(g[f] - ref[0])) < 2e-4

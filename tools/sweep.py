@@ -54,6 +54,37 @@ def main():
     torch.cuda.set_stream(torch.cuda.Stream())
     for kind in a.kinds.split(","):
         for n in sizes:
+            if kind == "stft":
+                # fused spectrogram: 64 Mi samples, hop = n/4, hann; bytes = samples read once + dB output written once
+                if n < 64:
+                    continue
+                ns = (1 << 26)
+                sp = wf.Spectrogram(ns, n, n // 4, "hann", 1, flags=C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+                x = torch.rand(ns, device=dev) * 2 - 1
+                out = torch.empty(sp.numFrames * sp.numBins, device=dev)
+                s_ = torch.cuda.current_stream().cuda_stream
+                for _ in range(3):
+                    sp.run_device(x.data_ptr(), out.data_ptr(), s_)
+                torch.cuda.synchronize()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+                ev[0].record()
+                for i in range(10):
+                    sp.run_device(x.data_ptr(), out.data_ptr(), s_)
+                    ev[i + 1].record()
+                torch.cuda.synchronize()
+                ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(10))
+                med = ts[5]
+                nbytes = sp.algorithmic_bytes()
+                rec = {"kind": kind, "n": n, "batch": sp.numFrames, "variant": "k_stft", "ms": round(med, 4), "ms_best": round(ts[0], 4),
+                       "Mtransforms_s": round(sp.numFrames / med / 1e3, 2), "GBs": round(nbytes / med / 1e6, 1),
+                       "frac": round(nbytes / med / 1e6 / PEAK, 3), "inverse": False}
+                line = json.dumps(rec)
+                print(line, flush=True)
+                outf.write(line + "\n")
+                sp.dispose()
+                del x, out
+                torch.cuda.empty_cache()
+                continue
             f64 = kind.endswith("f64")
             e = 8 if f64 else 4
             if kind.startswith("c2c"):

@@ -7,6 +7,7 @@ the build image has no JS runtime, and binds the very same C ABI (include/watfft
 """
 from . import _cabi
 from ._cabi import WatFFTError, build
+from .stft import Spectrogram, generateSpectrogram
 from .contexts import (
     createFFT, createFFTf32, createRFFT, createRFFTf32,
     createFFTf32Split, createRFFTf32Split, SplitExportsFacade, Plan,
@@ -15,5 +16,5 @@ from .contexts import (
 __all__ = [
     "createFFT", "createFFTf32", "createRFFT", "createRFFTf32",
     "createFFTf32Split", "createRFFTf32Split", "SplitExportsFacade", "Plan",
-    "WatFFTError", "build", "_cabi",
+    "Spectrogram", "generateSpectrogram", "WatFFTError", "build", "_cabi",
 ]

@@ -50,7 +50,20 @@ SYMBOLS = {
     "wfb_plan_algorithmic_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
     "wfb_kernel_launch_count": (ctypes.c_ulonglong, []),
     "wfb_reference_twiddles": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2),
+    "wfb_stft_create": (ctypes.c_void_p, [ctypes.c_int] * 4 + [ctypes.c_long, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                           ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "wfb_stft_destroy": (None, [ctypes.c_void_p]),
+    "wfb_stft_frames": (ctypes.c_long, [ctypes.c_void_p]),
+    "wfb_stft_bins": (ctypes.c_int, [ctypes.c_void_p]),
+    "wfb_stft_host_samples": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "wfb_stft_host_output": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "wfb_stft_output_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "wfb_stft_exec": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "wfb_stft_exec_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "wfb_stft_algorithmic_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
 }
+WINDOWS = {"hann": 0, "hamming": 1, "blackman": 2, "blackmanHarris": 3, "rectangular": 4}
+STFT_DB, STFT_COMPLEX = 0, 1
 
 _lib = None
 

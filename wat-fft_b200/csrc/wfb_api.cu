@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,17 @@ cudaError_t launch_grid(const void *kernel, size_t smem, int threads, long ctas,
     cudaError_t e = configure(kernel, smem, threads, &resident);
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&p};
+    e = cudaLaunchKernel(kernel, dim3((unsigned)ctas), dim3(threads), args, smem, s);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long ctas, void *params, cudaStream_t s) {
+    if (!kernel) return cudaErrorInvalidDeviceFunction;
+    int resident;
+    cudaError_t e = configure(kernel, smem, threads, &resident);
+    if (e != cudaSuccess) return e;
+    void *args[] = {params};
     e = cudaLaunchKernel(kernel, dim3((unsigned)ctas), dim3(threads), args, smem, s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e != cudaSuccess ? e : cudaGetLastError();
@@ -479,6 +491,143 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
         }
     }
     if (flags & WFB_SYNC) CK(cudaStreamSynchronize(pl->stream));
+    return WFB_OK;
+}
+
+}  // extern "C"
+
+
+// ----------------------------------------------------------------------------------------
+// batched STFT front-end
+// ----------------------------------------------------------------------------------------
+struct wfb_stft {
+    int fft_size, wsize, hop, mode, device, flags;
+    long num_samples, frames;
+    const StftVariant *variant;
+    void *d_tw, *d_rtw, *d_window, *d_samples, *d_out;
+    void *h_samples, *h_out;
+    size_t out_bytes;
+    float db_floor, inv_range;
+    cudaStream_t stream;
+};
+
+// WINDOW_FUNCTIONS of playground/src/spectrogram.js:1-25, evaluated in double like the JS, stored as f32
+static double window_value(int type, int i, int n) {
+    const double x = 2.0 * M_PI * i / (n - 1);
+    switch (type) {
+        case WFB_WINDOW_HAMMING: return 0.54 - 0.46 * cos(x);
+        case WFB_WINDOW_BLACKMAN: return 0.42 - 0.5 * cos(x) + 0.08 * cos(2 * x);
+        case WFB_WINDOW_BLACKMAN_HARRIS: return 0.35875 - 0.48829 * cos(x) + 0.14128 * cos(2 * x) - 0.01168 * cos(3 * x);
+        case WFB_WINDOW_RECTANGULAR: return 1.0;
+        default: return 0.5 * (1.0 - cos(x));
+    }
+}
+
+static int stft_init(wfb_stft *st) {
+    CK(cudaSetDevice(st->device));
+    CK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    const int n = st->fft_size, m = n / 2;
+    const StftVariant &v = *st->variant;
+    std::vector<float> bre, bim, fwd, rre, rim, packed, win(st->wsize);
+    base_twiddles<float>(TW_F32_SPLIT, m, m, bre, bim);
+    stage_tables<float>(v.radices, m, bre, bim, false, fwd);
+    if ((ilog2(m) & 1) && m >= 32 && v.radices.size() >= 2 && v.radices[0] == 2 && v.radices[1] == 4) {
+        const float c = 0.7071067811865476f;      // rfft_split's exact W_8 opening (see upload_tables)
+        const float w[3][2] = {{c, -c}, {0.f, -1.f}, {-c, -c}};
+        for (int mm = 0; mm < 3; mm++) { fwd[2 + 2 * (mm * 2 + 1)] = w[mm][0]; fwd[2 + 2 * (mm * 2 + 1) + 1] = w[mm][1]; }
+    }
+    base_twiddles<float>(TW_F32_SPLIT, n, m + 1, rre, rim);
+    for (int k = 0; k <= m; k++) { packed.push_back(rre[k]); packed.push_back(rim[k]); }
+    for (int i = 0; i < st->wsize; i++) win[i] = (float)window_value(st->mode >> 8, i, st->wsize);
+    auto up = [&](void **d, const std::vector<float> &h) -> int {
+        CK(cudaMalloc(d, h.size() * sizeof(float)));
+        CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return WFB_OK;
+    };
+    int rc;
+    if ((rc = up(&st->d_tw, fwd)) || (rc = up(&st->d_rtw, packed)) || (rc = up(&st->d_window, win))) return rc;
+    if (!(st->flags & WFB_PLAN_NO_DEVICE_BUFFERS)) {
+        if (cudaMalloc(&st->d_samples, st->num_samples * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+        if (cudaMalloc(&st->d_out, st->out_bytes) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+    }
+    if (!(st->flags & WFB_PLAN_NO_HOST_BUFFERS)) {
+        if (cudaHostAlloc(&st->h_samples, st->num_samples * sizeof(float), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+        if (cudaHostAlloc(&st->h_out, st->out_bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+        memset(st->h_samples, 0, st->num_samples * sizeof(float));
+        memset(st->h_out, 0, st->out_bytes);
+    }
+    return WFB_OK;
+}
+
+extern "C" {
+
+wfb_stft *wfb_stft_create(int fft_size, int zero_padding, int hop, int window_type, long num_samples, int mode,
+                          float gain_db, float range_db, int device, int flags, int *err) {
+    int dummy;
+    if (!err) err = &dummy;
+    if (!is_pow2(fft_size) || fft_size < 64 || fft_size > 8192) { *err = WFB_ERR_BAD_SIZE; return nullptr; }
+    if (zero_padding < 1 || !is_pow2(zero_padding) || zero_padding > fft_size / 2 || hop < 1 ||
+        window_type < 0 || window_type > WFB_WINDOW_RECTANGULAR || (mode != WFB_STFT_DB && mode != WFB_STFT_COMPLEX) ||
+        !(range_db > 0.0f)) { *err = WFB_ERR_BAD_ARG; return nullptr; }
+    const int wsize = fft_size / zero_padding;
+    if (num_samples < wsize) { *err = WFB_ERR_BAD_ARG; return nullptr; }      // "Audio too short" (spectrogram.js:299-301)
+    *err = check_device(device);
+    if (*err) return nullptr;
+    wfb_stft *st = new wfb_stft();
+    st->fft_size = fft_size; st->wsize = wsize; st->hop = hop; st->device = device; st->flags = flags;
+    st->mode = mode | (window_type << 8);
+    st->num_samples = num_samples;
+    st->frames = (num_samples - wsize) / hop + 1;
+    st->db_floor = gain_db - range_db;
+    st->inv_range = 1.0f / range_db;
+    st->out_bytes = (size_t)st->frames * (fft_size / 2 + 1) * sizeof(float) * (mode == WFB_STFT_COMPLEX ? 2 : 1);
+    for (const StftVariant &v : variants_stft()) if (v.core_n == fft_size / 2) st->variant = &v;
+    if (!st->variant) { *err = WFB_ERR_BAD_SIZE; delete st; return nullptr; }
+    *err = stft_init(st);
+    if (*err) { wfb_stft_destroy(st); return nullptr; }
+    return st;
+}
+
+void wfb_stft_destroy(wfb_stft *st) {
+    if (!st) return;
+    cudaSetDevice(st->device);
+    if (st->stream) { cudaStreamSynchronize(st->stream); cudaStreamDestroy(st->stream); }
+    void *d[] = {st->d_tw, st->d_rtw, st->d_window, st->d_samples, st->d_out};
+    for (void *p : d) if (p) cudaFree(p);
+    if (st->h_samples) cudaFreeHost(st->h_samples);
+    if (st->h_out) cudaFreeHost(st->h_out);
+    delete st;
+}
+
+long wfb_stft_frames(wfb_stft *st) { return st ? st->frames : 0; }
+int wfb_stft_bins(wfb_stft *st) { return st ? st->fft_size / 2 + 1 : 0; }
+void *wfb_stft_host_samples(wfb_stft *st) { return st ? st->h_samples : nullptr; }
+void *wfb_stft_host_output(wfb_stft *st) { return st ? st->h_out : nullptr; }
+size_t wfb_stft_output_bytes(wfb_stft *st) { return st ? st->out_bytes : 0; }
+size_t wfb_stft_algorithmic_bytes(wfb_stft *st) { return st ? (size_t)st->num_samples * sizeof(float) + st->out_bytes : 0; }
+
+int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void *stream) {
+    if (!st || !d_samples || !d_out) return WFB_ERR_BAD_ARG;
+    CK(cudaSetDevice(st->device));
+    StftParams sp;
+    sp.samples = d_samples; sp.window = (const float *)st->d_window; sp.out = d_out;
+    sp.tw = st->d_tw; sp.rtw = st->d_rtw;
+    sp.frames = st->frames; sp.hop = st->hop; sp.wsize = st->wsize; sp.mode = st->mode & 0xFF;
+    sp.db_floor = st->db_floor; sp.inv_range = st->inv_range; sp.inv_half_n = 2.0f / (float)st->fft_size;
+    cudaError_t e = st->variant->launch(sp, stream ? (cudaStream_t)stream : st->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "stft launch");
+    return WFB_OK;
+}
+
+int wfb_stft_exec(wfb_stft *st, int flags) {
+    if (!st || !st->d_samples) return WFB_ERR_BAD_ARG;
+    if ((flags & (WFB_STAGE_H2D | WFB_STAGE_D2H)) && !st->h_samples) return WFB_ERR_NO_HOST_BUFFERS;
+    CK(cudaSetDevice(st->device));
+    if (flags & WFB_STAGE_H2D) CK(cudaMemcpyAsync(st->d_samples, st->h_samples, st->num_samples * sizeof(float), cudaMemcpyHostToDevice, st->stream));
+    int rc = wfb_stft_exec_device(st, (const float *)st->d_samples, st->d_out, nullptr);
+    if (rc) return rc;
+    if (flags & WFB_STAGE_D2H) CK(cudaMemcpyAsync(st->h_out, st->d_out, st->out_bytes, cudaMemcpyDeviceToHost, st->stream));
+    if (flags & WFB_SYNC) CK(cudaStreamSynchronize(st->stream));
     return WFB_OK;
 }
 

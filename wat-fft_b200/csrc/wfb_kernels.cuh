@@ -1239,4 +1239,96 @@ __global__ void __launch_bounds__(X, MINB) k_c2r_tile(KParams p) {
     }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Batched STFT front-end: the reference's only batched caller is the spectrogram loop
+// of playground/src/spectrogram.js:281-360 -- per frame: slice `window` samples at `frame*hop`,
+// multiply by the window function, zero-pad to the FFT size, r2c, then |X| -> dB -> [0,1].
+// Here the frame gather + window multiply + zero padding are fused into the r2c load stage and the
+// magnitude/dB/normalise step into its store stage, so a spectrogram is ONE kernel: the overlapping
+// frames are read once from HBM (L2 serves the overlap) and only (N/2+1) floats per frame are written.
+// PL describes the M = N/2 point complex core, exactly as in k_r2c.
+// ----------------------------------------------------------------------------------------
+struct StftParams {
+    const float *samples;      // [num_samples]
+    const float *window;       // [wsize] window function values (f32), host-built
+    void *out;                 // MODE_DB: float [frames][M+1];  MODE_COMPLEX: float2 [frames][M+1]
+    const void *tw, *rtw;      // stage tables / W_N^k of the r2c core
+    long frames;
+    int hop, wsize, mode;
+    float db_floor;            // gain - range
+    float inv_range;           // 1 / range
+    float inv_half_n;          // 1 / (N/2)
+};
+enum { STFT_MODE_DB = 0, STFT_MODE_COMPLEX = 1 };
+
+__device__ __forceinline__ float stft_db(float re, float im, const StftParams &sp) {
+    // computeMagnitude + magnitudeToDb + normalisation (spectrogram.js:78-96, :343-352)
+    const float mag = sqrtf(re * re + im * im);
+    const float db = 20.0f * log10f(mag * sp.inv_half_n + 1e-10f);
+    const float v = (db - sp.db_floor) * sp.inv_range;
+    return fminf(1.0f, fmaxf(0.0f, v));
+}
+
+template <class PL, int X, int PADQ, int MINB>
+__global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
+    static_assert(PL::valid(), "plan does not factor N");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using R = float;
+    constexpr int M = PL::N;
+    constexpr int LAST = PL::npass() - 1;
+    const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
+    const long frame = (long)blockIdx.x * X + xi;
+    const bool active = frame < sp.frames;
+    cx<R> *sm = reinterpret_cast<cx<R> *>(smem_raw) + (size_t)xi * padded_size<PADQ>(M);
+    const float2 *tw = reinterpret_cast<const float2 *>(sp.tw);
+    const float2 *rtw = reinterpret_cast<const float2 *>(sp.rtw);
+    cx<R> x[PL::E];
+
+    {   // gather + window + zero-pad: z[p] = (s[off+2p] w[2p], s[off+2p+1] w[2p+1])
+        const float *s = sp.samples + (active ? frame * (long)sp.hop : 0);
+        static_for<PL::E>([&](auto E_) {
+            CIDX(e, E_);
+            const int i0 = 2 * (tid + e * PL::T);
+            float a = 0.0f, b = 0.0f;
+            if (active && i0 < sp.wsize) a = __ldg(s + i0) * __ldg(sp.window + i0);
+            if (active && i0 + 1 < sp.wsize) b = __ldg(s + i0 + 1) * __ldg(sp.window + i0 + 1);
+            x[e] = mk<R>(a, b);
+        });
+    }
+    run_all<R, PL, PADQ, X, false>(x, tw, sm, tid, xi, false);
+    if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
+    spill_outputs<R, PL, LAST, PADQ>(x, sm, tid);
+    sync_transform<PL::T, X>(xi);
+    if (!active) return;
+
+    constexpr int HALF = M / 2;
+    constexpr int PER = (HALF + PL::T - 1) / PL::T;
+    float *odb = reinterpret_cast<float *>(sp.out) + frame * (M + 1);
+    float2 *ocx = reinterpret_cast<float2 *>(sp.out) + frame * (M + 1);
+    auto emit = [&](int k, cx<R> v) {
+        if (sp.mode == STFT_MODE_COMPLEX) st_stream(ocx + k, make_float2(v.x, v.y));
+        else st_stream(odb + k, k < 3 ? 0.0f : stft_db(v.x, v.y, sp));      // DC and near-DC bins zeroed (:338-342)
+    };
+    static_for<PER>([&](auto I_) {
+        CIDX(i, I_);
+        const int k = tid + i * PL::T;
+        if (k < HALF) {
+            if (i == 0 && k == 0) {
+                const cx<R> z0 = sm[0];
+                emit(0, mk<R>(z0.x + z0.y, 0.0f));
+                emit(M, mk<R>(z0.x - z0.y, 0.0f));
+                emit(HALF, RealPost<R>::middle(sm[pad_idx<PADQ>(HALF)], ld_tw(rtw + HALF), M));
+            } else {
+                const cx<R> z = sm[pad_idx<PADQ>(k)], zm = sm[pad_idx<PADQ>(M - k)];
+                cx<R> xk, xm;
+                const twd<R> w = ld_tw(rtw + k);
+                RealPost<R>::pair(z, zm, w, w, xk, xm);
+                emit(k, xk);
+                emit(M - k, xm);
+            }
+        }
+    });
+}
+
 }  // namespace wfb

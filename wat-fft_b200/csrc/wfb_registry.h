@@ -137,6 +137,19 @@ template <class PL, int X, int MINB> struct RealTileLaunchers {
     }
 };
 
+// fused STFT (frame gather + window + r2c + magnitude/dB)
+typedef cudaError_t (*stft_launch_fn)(const StftParams &sp, cudaStream_t s);
+struct StftVariant { const char *name; int core_n; std::vector<int> radices; stft_launch_fn launch; };
+cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long ctas, void *params, cudaStream_t s);
+const std::vector<StftVariant> &variants_stft();
+template <class PL, int X, int MINB> struct StftLaunchers {
+    static constexpr size_t smem = sizeof(cx<float>) * (size_t)padded_size<PADQ>(PL::N) * X;
+    static cudaError_t launch(const StftParams &sp, cudaStream_t s) {
+        return launch_grid_raw((const void *)k_stft<PL, X, PADQ, MINB>, smem, PL::T * X, (sp.frames + X - 1) / X, (void *)&sp, s);
+    }
+    static StftVariant make(const char *name) { return StftVariant{name, PL::N, plan_radices<PL>(), &launch}; }
+};
+
 #define XROWS(T) ((T) >= 256 ? 1 : 256 / (T))
 
 // f32 core plans: the reference's split-core stage structure (radix-4, leading radix-2 for odd log2)
