@@ -1287,12 +1287,21 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
 
     {   // gather + window + zero-pad: z[p] = (s[off+2p] w[2p], s[off+2p+1] w[2p+1])
         const float *s = sp.samples + (active ? frame * (long)sp.hop : 0);
+        const bool vec = ((sp.hop | sp.wsize) & 1) == 0;    // even hop: frame starts are 8-byte aligned
         static_for<PL::E>([&](auto E_) {
             CIDX(e, E_);
             const int i0 = 2 * (tid + e * PL::T);
             float a = 0.0f, b = 0.0f;
-            if (active && i0 < sp.wsize) a = __ldg(s + i0) * __ldg(sp.window + i0);
-            if (active && i0 + 1 < sp.wsize) b = __ldg(s + i0 + 1) * __ldg(sp.window + i0 + 1);
+            if (vec) {
+                if (active && i0 < sp.wsize) {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(s + i0));
+                    const float2 w = __ldg(reinterpret_cast<const float2 *>(sp.window + i0));
+                    a = v.x * w.x; b = v.y * w.y;
+                }
+            } else {
+                if (active && i0 < sp.wsize) a = __ldg(s + i0) * __ldg(sp.window + i0);
+                if (active && i0 + 1 < sp.wsize) b = __ldg(s + i0 + 1) * __ldg(sp.window + i0 + 1);
+            }
             x[e] = mk<R>(a, b);
         });
     }
