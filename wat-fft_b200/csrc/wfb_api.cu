@@ -86,6 +86,18 @@ cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long c
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+cudaError_t launch_persistent_raw(const void *kernel, size_t smem, int threads, long work_items, void *params, cudaStream_t s) {
+    if (!kernel) return cudaErrorInvalidDeviceFunction;
+    int resident;
+    cudaError_t e = configure(kernel, smem, threads, &resident);
+    if (e != cudaSuccess) return e;
+    long grid = work_items < resident ? work_items : resident;
+    void *args[] = {params};
+    e = cudaLaunchKernel(kernel, dim3((unsigned)grid), dim3(threads), args, smem, s);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 // persistent kernels: grid = min(work items, CTAs resident on the whole GPU)
 cudaError_t launch_persistent(const void *kernel, size_t smem, int threads, long work_items, const KParams &p, cudaStream_t s) {
     if (!kernel) return cudaErrorInvalidDeviceFunction;
@@ -614,7 +626,10 @@ int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void
     sp.tw = st->d_tw; sp.rtw = st->d_rtw;
     sp.frames = st->frames; sp.hop = st->hop; sp.wsize = st->wsize; sp.mode = st->mode & 0xFF;
     sp.db_floor = st->db_floor; sp.inv_range = st->inv_range; sp.inv_half_n = 2.0f / (float)st->fft_size;
-    cudaError_t e = st->variant->launch(sp, stream ? (cudaStream_t)stream : st->stream);
+    // frames are TMA-copyable when their starts are 16-byte aligned (hop % 4 == 0, aligned base)
+    static const int pipe_min = [] { const char *e = getenv("WFB_STFT_PIPE_MIN_N"); return e ? atoi(e) : 8192; }();
+    const bool pipe = st->fft_size >= pipe_min && st->hop % 4 == 0 && st->wsize % 4 == 0 && ((uintptr_t)d_samples % 16) == 0;
+    cudaError_t e = (pipe ? st->variant->launch_pipe : st->variant->launch)(sp, stream ? (cudaStream_t)stream : st->stream);
     if (e != cudaSuccess) return cuda_fail(e, "stft launch");
     return WFB_OK;
 }

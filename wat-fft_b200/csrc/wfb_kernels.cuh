@@ -196,17 +196,22 @@ __device__ __forceinline__ void twiddled_r4(const cx<R> &A, const cx<R> &B, cons
     t0 = cadd<R>(A, wc); t1 = csub<R>(A, wc);
     t2 = cadd<R>(wb, wd); t3 = csub<R>(wb, wd);
 }
-// f32 scalar lanes: FMA-fused form, 16 instead of 20 instructions (negated operands are free SASS
-// modifiers): t0 and t2 as FMA chains, then t1 = 2A - t0 and t3 = 2*(w1*B) - t2.
-__device__ __forceinline__ void twiddled_r4(const cx<float> &A, const cx<float> &B, const cx<float> &C, const cx<float> &D,
-                                            const twd<float> &w1, const twd<float> &w2, const twd<float> &w3,
-                                            cx<float> &t0, cx<float> &t1, cx<float> &t2, cx<float> &t3) {
-    const cx<float> wb = cmul<float>(w1, B);
-    t0 = mk<float>(fmaf(w2.ny, C.y, fmaf(w2.x, C.x, A.x)), fmaf(w2.y, C.x, fmaf(w2.x, C.y, A.y)));
-    t2 = mk<float>(fmaf(w3.ny, D.y, fmaf(w3.x, D.x, wb.x)), fmaf(w3.y, D.x, fmaf(w3.x, D.y, wb.y)));
-    t1 = mk<float>(fmaf(2.0f, A.x, -t0.x), fmaf(2.0f, A.y, -t0.y));
-    t3 = mk<float>(fmaf(2.0f, wb.x, -t2.x), fmaf(2.0f, wb.y, -t2.y));
-}
+// Scalar lanes (f32 and f64): FMA-fused form, 16 instead of 20 instructions (negated operands are free
+// SASS modifiers): t0 and t2 as FMA chains, then t1 = 2A - t0 and t3 = 2*(w1*B) - t2.  Same table
+// entries on the same operands; only the rounding points move (f64 parity stays ~1 % of its bound).
+#define WFB_FUSED_R4(T)                                                                                      \
+    __device__ __forceinline__ void twiddled_r4(const cx<T> &A, const cx<T> &B, const cx<T> &C, const cx<T> &D, \
+                                                const twd<T> &w1, const twd<T> &w2, const twd<T> &w3,         \
+                                                cx<T> &t0, cx<T> &t1, cx<T> &t2, cx<T> &t3) {                 \
+        const cx<T> wb = cmul<T>(w1, B);                                                                     \
+        t0 = mk<T>(rfma(w2.ny, C.y, rfma(w2.x, C.x, A.x)), rfma(w2.y, C.x, rfma(w2.x, C.y, A.y)));           \
+        t2 = mk<T>(rfma(w3.ny, D.y, rfma(w3.x, D.x, wb.x)), rfma(w3.y, D.x, rfma(w3.x, D.y, wb.y)));         \
+        t1 = mk<T>(rfma(T(2), A.x, -t0.x), rfma(T(2), A.y, -t0.y));                                          \
+        t3 = mk<T>(rfma(T(2), wb.x, -t2.x), rfma(T(2), wb.y, -t2.y));                                        \
+    }
+WFB_FUSED_R4(float)
+WFB_FUSED_R4(double)
+#undef WFB_FUSED_R4
 
 // ----------------------------------------------------------------------------------------
 // one fused pass over the E register-resident values of a thread
@@ -1264,8 +1269,9 @@ enum { STFT_MODE_DB = 0, STFT_MODE_COMPLEX = 1 };
 
 __device__ __forceinline__ float stft_db(float re, float im, const StftParams &sp) {
     // computeMagnitude + magnitudeToDb + normalisation (spectrogram.js:78-96, :343-352)
+    // 20*log10(v) = 6.0206*log2(v): one MUFU.LG2 instead of the ~25-instruction log10f (|error| < 1e-5 dB)
     const float mag = sqrtf(re * re + im * im);
-    const float db = 20.0f * log10f(mag * sp.inv_half_n + 1e-10f);
+    const float db = 6.0205999132796239f * __log2f(mag * sp.inv_half_n + 1e-10f);
     const float v = (db - sp.db_floor) * sp.inv_range;
     return fminf(1.0f, fmaxf(0.0f, v));
 }
@@ -1338,6 +1344,107 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
             }
         }
     });
+}
+
+
+// TMA-pipelined STFT: frames are rows at `hop` stride in the sample array, so when hop is a
+// multiple of 4 samples (16-byte aligned frame starts) each frame is one bulk copy into a padded
+// smem row, prefetched one tile ahead exactly like k_real_pipe's row-copy mode.
+template <class PL, int X, int PADQ, int MINB>
+__global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
+    static_assert(PL::valid() && PL::T * X >= 32, "needs a full issuing warp");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using R = float;
+    constexpr int M = PL::N;
+    constexpr int LAST = PL::npass() - 1;
+    constexpr int RSTR = M + M / 16;                   // smem row stride (float2): rows T banks apart
+    constexpr size_t BUF = real_pipe_buf_bytes<R, PL, PADQ, X, false>();
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
+    const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
+    const float2 *tw = reinterpret_cast<const float2 *>(sp.tw);
+    const float2 *rtw = reinterpret_cast<const float2 *>(sp.rtw);
+    const long tiles = (sp.frames + X - 1) / X;
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar + 0, 1);
+        mbar_init(mbar + 1, 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    auto issue = [&](long tile, int st) {
+        if (threadIdx.x < 32) {
+            const long f0 = tile * X;
+            const int rows = (sp.frames - f0 < X) ? (int)(sp.frames - f0) : X;
+            const uint32_t rowb = (uint32_t)(sp.wsize * sizeof(float));
+            if (threadIdx.x == 0) mbar_expect_tx(mbar + st, rows * rowb);
+            __syncwarp();
+            for (int r = threadIdx.x; r < rows; r += 32)
+                tma_load_1d(smem_raw + st * BUF + (size_t)r * RSTR * sizeof(float2), sp.samples + (f0 + r) * (long)sp.hop, rowb, mbar + st);
+        }
+    };
+
+    long tile = blockIdx.x;
+    if (tile < tiles) issue(tile, 0);
+    cx<R> x[PL::E];
+    const float2 *win = reinterpret_cast<const float2 *>(sp.window);
+    for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
+        const int st = it & 1;
+        fence_proxy_async();
+        __syncthreads();
+        if (tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        mbar_wait(mbar + st, (it >> 1) & 1);
+        unsigned char *buf = smem_raw + st * BUF;
+        const long frame = tile * X + xi;
+        const bool active = frame < sp.frames;
+        cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(M);
+        const float2 *raw = reinterpret_cast<const float2 *>(buf) + (size_t)xi * RSTR;
+
+        static_for<PL::E>([&](auto E_) {               // window multiply + zero padding on the way to registers
+            CIDX(e, E_);
+            const int pidx = tid + e * PL::T;
+            float a = 0.0f, b = 0.0f;
+            if (active && 2 * pidx < sp.wsize) {
+                const float2 v = raw[pidx], w = __ldg(win + pidx);
+                a = v.x * w.x; b = v.y * w.y;
+            }
+            x[e] = mk<R>(a, b);
+        });
+        __syncthreads();                               // raw rows and padded scratch alias
+        run_all<R, PL, PADQ, X, false>(x, tw, scratch, tid, xi, false);
+        if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
+        spill_outputs<R, PL, LAST, PADQ>(x, scratch, tid);
+        sync_transform<PL::T, X>(xi);
+        if (active) {
+            constexpr int HALF = M / 2;
+            constexpr int PER = (HALF + PL::T - 1) / PL::T;
+            float *odb = reinterpret_cast<float *>(sp.out) + frame * (M + 1);
+            float2 *ocx = reinterpret_cast<float2 *>(sp.out) + frame * (M + 1);
+            auto emit = [&](int k, cx<R> v) {
+                if (sp.mode == STFT_MODE_COMPLEX) st_stream(ocx + k, make_float2(v.x, v.y));
+                else st_stream(odb + k, k < 3 ? 0.0f : stft_db(v.x, v.y, sp));
+            };
+            static_for<PER>([&](auto I_) {
+                CIDX(i, I_);
+                const int k = tid + i * PL::T;
+                if (k < HALF) {
+                    if (i == 0 && k == 0) {
+                        const cx<R> z0 = scratch[0];
+                        emit(0, mk<R>(z0.x + z0.y, 0.0f));
+                        emit(M, mk<R>(z0.x - z0.y, 0.0f));
+                        emit(HALF, RealPost<R>::middle(scratch[pad_idx<PADQ>(HALF)], ld_tw(rtw + HALF), M));
+                    } else {
+                        const cx<R> z = scratch[pad_idx<PADQ>(k)], zm = scratch[pad_idx<PADQ>(M - k)];
+                        cx<R> xk, xm;
+                        const twd<R> w = ld_tw(rtw + k);
+                        RealPost<R>::pair(z, zm, w, w, xk, xm);
+                        emit(k, xk);
+                        emit(M - k, xm);
+                    }
+                }
+            });
+        }
+    }
 }
 
 }  // namespace wfb
