@@ -189,8 +189,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+        # NCCL prints its version banner on stdout; keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     n_gpus = world
     rc = lib.wfb_require_b200(local)
