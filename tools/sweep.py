@@ -22,8 +22,32 @@ except Exception:
     pass
 
 
+SUSTAIN = 0.0
+
+
 def time_plan(plan, direction, d_in, d_out, iters=10, warm=3):
     s = torch.cuda.current_stream().cuda_stream
+    if SUSTAIN > 0:
+        # steady state under the power cap: run for SUSTAIN seconds, time the second half
+        import time as _t
+        t0 = _t.perf_counter()
+        n = 0
+        while _t.perf_counter() - t0 < SUSTAIN / 2:
+            for _ in range(20):
+                plan.exec_device(direction, d_in, d_out, s)
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = _t.perf_counter()
+        while _t.perf_counter() - t0 < SUSTAIN / 2:
+            for _ in range(20):
+                plan.exec_device(direction, d_in, d_out, s)
+            n += 20
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        return ms, ms
     assert s != 0, "time on a non-default stream: stream 0 means 'the plan's own stream' to the C ABI"
     for _ in range(warm):
         plan.exec_device(direction, d_in, d_out, s)
@@ -44,8 +68,11 @@ def main():
     ap.add_argument("--kinds", default="c2c_split,c2c_il,r2c,c2r,c2c_f64,r2c_f64")
     ap.add_argument("--sizes", default="16,32,64,128,256,512,1024,2048,4096")
     ap.add_argument("--inverse", action="store_true")
+    ap.add_argument("--sustain", type=float, default=0.0, help="seconds per variant of back-to-back launches (power-capped steady state)")
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "sweep.jsonl"))
     a = ap.parse_args()
+    global SUSTAIN
+    SUSTAIN = a.sustain
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     sizes = [int(x) for x in a.sizes.split(",")]
     total = int(a.gib * (1 << 30))

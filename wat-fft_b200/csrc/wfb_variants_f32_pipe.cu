@@ -5,10 +5,11 @@ namespace wfb {
 #define VPR(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, true>::make(#PL "_pipe" #X "_rc", PRIO)
 #define VP2(PL, X, MINB, PRIO) PipeLaunchers<f32x2, PL, X, MINB>::make(#PL "_pipe" #X "_x2", PRIO)
 const std::vector<Variant> &variants_f32_pipe() {
-    // priorities from gpurun_out/sweep7 (profiles/r01_sweep.md): higher = default
+    // priorities from the SUSTAINED sweep (tools/sweep.py --sustain 0.6, power-capped clocks, which is what
+    // bench.py's long step sees; the burst ranking differs at N = 256 and 1024): higher = default
     static const std::vector<Variant> v = {
-        VP(F32_128, 16, 2, 30), VP(F32_256, 8, 2, 30), VP(F32_512, 4, 2, 31),
-        VP(F32_1024, 2, 2, 33), VP(F32_1024, 1, 8, 31),
+        VP(F32_128, 16, 2, 30), VP(F32_256, 8, 2, 36), VP(F32_512, 4, 2, 31),
+        VP(F32_1024, 2, 2, 31), VP(F32_1024, 1, 8, 33),
         VP(F32_2048, 1, 4, 30), VP(F32_4096, 1, 2, 30), VP(F32_8192, 1, 1, 30),
         VPR(F32_128, 16, 2, 34), VPR(F32_256, 16, 2, 35),
         VP2(F32_128, 16, 2, 29), VP2(F32_256, 8, 2, 33), VP2(F32_512, 4, 2, 29), VP2(F32_512, 1, 4, 32),
