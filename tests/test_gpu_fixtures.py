@@ -223,3 +223,33 @@ def test_staged_pipeline_large_batch(wf, oracle):
     for r in rows:
         assert np.max(np.abs(t[r] - xs[r])) < 1e-4
     rc.dispose()
+
+
+def test_exec_device_misaligned_pointers_fall_back(wf, oracle):
+    """Caller-supplied device pointers that are only 4- or 8-byte aligned must not reach the TMA /
+    128-bit kernels: the plan serves them with the direct variant (same results)."""
+    import torch
+    C = wf._cabi
+    n, batch = 1024, 33
+    rng = np.random.default_rng(5)
+    re = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    im = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    pad = 1                                              # one float: 4-byte aligned, not 16
+    d_re = torch.zeros(batch * n + 8, device=dev)
+    d_im = torch.zeros(batch * n + 8, device=dev)
+    o_re, o_im = torch.zeros_like(d_re), torch.zeros_like(d_im)
+    d_re[pad:pad + batch * n] = torch.from_numpy(re.ravel()).to(dev)
+    d_im[pad:pad + batch * n] = torch.from_numpy(im.ravel()).to(dev)
+    plan = wf.Plan(C.C2C, C.F32, C.SPLIT, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    assert "pipe" in plan.variants()[0]                  # the default would be a TMA kernel
+    plan.exec_device(C.FORWARD, (d_re.data_ptr() + 4 * pad, d_im.data_ptr() + 4 * pad),
+                     (o_re.data_ptr() + 4 * pad, o_im.data_ptr() + 4 * pad))
+    plan.sync()
+    gr = o_re[pad:pad + batch * n].cpu().numpy().reshape(batch, n)
+    gi = o_im[pad:pad + batch * n].cpu().numpy().reshape(batch, n)
+    for r in (0, 16, batch - 1):
+        er, ei = oracle.fft_split_f32(re[r], im[r])
+        assert rel_err(np.r_[gr[r], gi[r]], np.r_[er, ei], np.r_[re[r], im[r]]) <= f32_bound(n)
+    assert float(o_re[0]) == 0.0 and float(o_re[pad + batch * n]) == 0.0     # nothing written outside
+    plan.destroy()

@@ -340,7 +340,12 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
             if (v.core_n == pl->core_n && (kind == WFB_C2C ? v.c2c != nullptr : v.r2c != nullptr)) pl->variants.push_back(&v);
     std::stable_sort(pl->variants.begin(), pl->variants.end(),
                      [](const Variant *a, const Variant *b) { return a->priority > b->priority; });
-    if (pl->variants.size() > 8) pl->variants.resize(8);
+    if (pl->variants.size() > 8) {          // keep the 7 best plus the least-demanding (direct) fallback
+        const Variant *fallback = pl->variants.back();
+        for (const Variant *v : pl->variants) if (v->align < fallback->align) fallback = v;
+        pl->variants.resize(7);
+        if (std::find(pl->variants.begin(), pl->variants.end(), fallback) == pl->variants.end()) pl->variants.push_back(fallback);
+    }
     for (size_t i = 0; i < pl->variants.size(); i++)
         if (pl->variants[i]->priority_inv > pl->variants[pl->variant_inv]->priority_inv) pl->variant_inv = (int)i;
     if (pl->variants.empty()) { *err = WFB_ERR_BAD_SIZE; delete pl; return nullptr; }
@@ -400,7 +405,21 @@ unsigned long long wfb_kernel_launch_count(void) { return g_launches.load(); }
 // launches the current variant over `rows` rows starting at the given plane pointers
 static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void *in1, void *out0, void *out1,
                        long rows, cudaStream_t s) {
-    const int vi = direction == WFB_INVERSE ? pl->variant_inv : pl->variant;
+    int vi = direction == WFB_INVERSE ? pl->variant_inv : pl->variant;
+    // The TMA / 128-bit kernels need 16-byte aligned planes (cudaMalloc gives 256).  Caller-supplied
+    // pointers that are less aligned are served by the first variant whose requirement they meet.
+    const uintptr_t bits = (uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)out0 | (uintptr_t)out1;
+    auto need = [&](const Variant *v) {
+        // direct kernels read split planes with scalar loads
+        return (v->align < 16 && pl->kind == WFB_C2C && pl->layout == WFB_SPLIT) ? (int)pl->elem : v->align;
+    };
+    if (bits & (uintptr_t)(need(pl->variants[vi]) - 1)) {
+        int alt = -1;
+        for (size_t i = 0; i < pl->variants.size() && alt < 0; i++)
+            if (!(bits & (uintptr_t)(need(pl->variants[i]) - 1))) alt = (int)i;
+        if (alt < 0) return WFB_ERR_BAD_ARG;
+        vi = alt;
+    }
     const Variant &v = *pl->variants[vi];
     KParams p;
     p.in0 = in0; p.in1 = in1; p.out0 = out0; p.out1 = out1;

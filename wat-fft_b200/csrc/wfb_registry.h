@@ -21,6 +21,8 @@ struct Variant {
     int lanes;         // batch rows per thread group: 2 for the packed-FP32 (f32x2) kernels
     int priority;      // larger = preferred default (set from measurements, profiles/)
     int priority_inv;  // same for the inverse direction (c2r / ifft); -1 = same as `priority`
+    int align;         // required alignment (bytes) of every plane pointer: 16 for the TMA / float4 kernels,
+                       // one complex value for the direct kernels (one scalar when the layout is split)
     std::vector<int> radices;
     launch_fn c2c, r2c, c2r;
 };
@@ -70,7 +72,7 @@ template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers
         return launch_grid((const void *)k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, ctas(batch), p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), &c2c, &r2c, &c2r};
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, 2 * (int)sizeof(typename RT<R>::scalar), plan_radices<PL>(), &c2c, &r2c, &c2r};
     }
 };
 
@@ -88,7 +90,7 @@ template <typename R, class PL, int X, int MINB, bool RC = false> struct PipeLau
         return launch_persistent(k, smem, PL::T * X, tiles(batch), p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), &c2c, nullptr, nullptr};
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), &c2c, nullptr, nullptr};
     }
 };
 
@@ -103,7 +105,7 @@ template <typename R, class PL, int X, int MINB, bool RC = false> struct RealPip
         return launch_persistent((const void *)k_real_pipe<R, PL, X, PADQ, true, MINB>, smem_i, PL::T * X, (batch + X - 1) / X, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), nullptr, &r2c, &c2r};
+        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 
@@ -119,7 +121,7 @@ template <class PL, int X, int MINB> struct TileLaunchers {
         return launch_grid(k, smem, X, (batch + X - 1) / X, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), &c2c, nullptr, nullptr};
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), &c2c, nullptr, nullptr};
     }
 };
 
@@ -133,7 +135,7 @@ template <class PL, int X, int MINB> struct RealTileLaunchers {
         return launch_grid((const void *)k_c2r_tile<PL, X, MINB>, smem, X, (batch + X - 1) / X, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, plan_radices<PL>(), nullptr, &r2c, &c2r};
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 

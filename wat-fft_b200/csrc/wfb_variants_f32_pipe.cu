@@ -12,7 +12,7 @@ const std::vector<Variant> &variants_f32_pipe() {
         VP(F32_1024, 2, 2, 31), VP(F32_1024, 1, 8, 33),
         VP(F32_2048, 1, 4, 30), VP(F32_4096, 1, 2, 30), VP(F32_8192, 1, 1, 30),
         VPR(F32_128, 16, 2, 34), VPR(F32_256, 16, 2, 35),
-        VP2(F32_128, 16, 2, 29), VP2(F32_256, 8, 2, 33), VP2(F32_512, 4, 2, 29), VP2(F32_512, 1, 4, 32),
+        VP2(F32_256, 8, 2, 33), VP2(F32_512, 1, 4, 32),
     };
     return v;
 }

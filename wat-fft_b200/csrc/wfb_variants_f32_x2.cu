@@ -4,7 +4,8 @@ namespace wfb {
 #define V(PL, MINB, PRIO) Launchers<f32x2, PL, XROWS(PL::T), MINB, true>::make(#PL "_x2", PRIO)
 const std::vector<Variant> &variants_f32_x2() {
     static const std::vector<Variant> v = {
-        V(F32_128, 2, 20), V(F32_256, 2, 20), V(F32_512, 2, 20), V(F32_1024, 2, 20), V(F32_2048, 2, 5), V(F32_4096, 2, 5),
+        V(F32_128, 2, 20), V(F32_256, 2, 20), V(F32_512, 2, 20), V(F32_1024, 2, 20),
+        // N >= 2048 removed: never within 10 % of the pipelined scalar kernels (profiles/r01_sweep.md)
     };
     return v;
 }
