@@ -77,16 +77,16 @@ template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers
 };
 
 // persistent TMA-pipelined c2c: grid = resident CTAs, each loops over tiles of X*LANES rows
-template <typename R, class PL, int X, int MINB, bool RC = false> struct PipeLaunchers {
-    static constexpr size_t smem = 2 * pipe_buf_bytes<R, PL, PADQ, X>() + 64;
+template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ> struct PipeLaunchers {
+    static constexpr size_t smem = 2 * pipe_buf_bytes<R, PL, PQ, X>() + 64;
     static constexpr int LANES = RT<R>::LANES;
     static long tiles(long batch) { return (batch + X * LANES - 1) / (X * LANES); }
     static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
         const void *k;
         if (io == IO_SPLIT)
-            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_SPLIT, true, MINB, RC> : (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_SPLIT, false, MINB, RC>;
+            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PQ, IO_SPLIT, true, MINB, RC> : (const void *)k_c2c_pipe<R, PL, X, PQ, IO_SPLIT, false, MINB, RC>;
         else
-            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_INTERLEAVED, true, MINB, RC> : (const void *)k_c2c_pipe<R, PL, X, PADQ, IO_INTERLEAVED, false, MINB, RC>;
+            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, true, MINB, RC> : (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, false, MINB, RC>;
         return launch_persistent(k, smem, PL::T * X, tiles(batch), p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1) {
@@ -177,6 +177,10 @@ using F32_8192 = Plan<8192, 512, 0x2, 0x44, 0x44, 0x44>;
 // experimental: 32 values per thread (two register blocks per pass), half the threads per transform
 using P32_4096_T128 = Plan<4096, 128, 0x44, 0x44, 0x44>;
 using P32_2048_T64 = Plan<2048, 64, 0x24, 0x44, 0x44>;
+// 64 values per thread: two passes, ONE shared-memory exchange (pad slot per 64 values: tools/bank_sim.py)
+using P64_4096 = Plan<4096, 64, 0x444, 0x444>;
+using P64_2048 = Plan<2048, 32, 0x244, 0x444>;
+using P64_1024 = Plan<1024, 16, 0x44, 0x444>;
 // thread-per-row plans for the tile kernels (whole transform in registers)
 using T32_32 = Plan<32, 1, 0x244>;
 using T32_64 = Plan<64, 1, 0x444>;
