@@ -338,8 +338,10 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
     for (const auto *fam : families)
         for (const Variant &v : *fam)
             if (v.core_n == pl->core_n && (kind == WFB_C2C ? v.c2c != nullptr : v.r2c != nullptr)) pl->variants.push_back(&v);
-    std::stable_sort(pl->variants.begin(), pl->variants.end(),
-                     [](const Variant *a, const Variant *b) { return a->priority > b->priority; });
+    const bool il = kind == WFB_C2C && layout == WFB_INTERLEAVED;
+    std::stable_sort(pl->variants.begin(), pl->variants.end(), [il](const Variant *a, const Variant *b) {
+        return (il ? a->priority_il : a->priority) > (il ? b->priority_il : b->priority);
+    });
     if (pl->variants.size() > 8) {          // keep the 7 best plus the least-demanding (direct) fallback
         const Variant *fallback = pl->variants.back();
         for (const Variant *v : pl->variants) if (v->align < fallback->align) fallback = v;
@@ -347,7 +349,7 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
         if (std::find(pl->variants.begin(), pl->variants.end(), fallback) == pl->variants.end()) pl->variants.push_back(fallback);
     }
     for (size_t i = 0; i < pl->variants.size(); i++)
-        if (pl->variants[i]->priority_inv > pl->variants[pl->variant_inv]->priority_inv) pl->variant_inv = (int)i;
+        if (!il && pl->variants[i]->priority_inv > pl->variants[pl->variant_inv]->priority_inv) pl->variant_inv = (int)i;
     if (pl->variants.empty()) { *err = WFB_ERR_BAD_SIZE; delete pl; return nullptr; }
     *err = plan_init(pl);
     if (*err) { wfb_plan_destroy(pl); return nullptr; }

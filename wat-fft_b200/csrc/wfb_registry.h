@@ -21,6 +21,7 @@ struct Variant {
     int lanes;         // batch rows per thread group: 2 for the packed-FP32 (f32x2) kernels
     int priority;      // larger = preferred default (set from measurements, profiles/)
     int priority_inv;  // same for the inverse direction (c2r / ifft); -1 = same as `priority`
+    int priority_il;   // same for interleaved c2c layouts; -1 = same as `priority`
     int align;         // required alignment (bytes) of every plane pointer: 16 for the TMA / float4 kernels,
                        // one complex value for the direct kernels (one scalar when the layout is split)
     std::vector<int> radices;
@@ -71,8 +72,8 @@ template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
         return launch_grid((const void *)k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, ctas(batch), p, s);
     }
-    static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, 2 * (int)sizeof(typename RT<R>::scalar), plan_radices<PL>(), &c2c, &r2c, &c2r};
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 2 * (int)sizeof(typename RT<R>::scalar), plan_radices<PL>(), &c2c, &r2c, &c2r};
     }
 };
 
@@ -89,8 +90,8 @@ template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ>
             k = dir ? (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, true, MINB, RC> : (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, false, MINB, RC>;
         return launch_persistent(k, smem, PL::T * X, tiles(batch), p, s);
     }
-    static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), &c2c, nullptr, nullptr};
     }
 };
 
@@ -104,8 +105,8 @@ template <typename R, class PL, int X, int MINB, bool RC = false> struct RealPip
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
         return launch_persistent((const void *)k_real_pipe<R, PL, X, PADQ, true, MINB>, smem_i, PL::T * X, (batch + X - 1) / X, p, s);
     }
-    static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 
@@ -120,8 +121,8 @@ template <class PL, int X, int MINB> struct TileLaunchers {
             k = dir ? (const void *)k_c2c_tile<float, PL, X, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_tile<float, PL, X, IO_INTERLEAVED, false, MINB>;
         return launch_grid(k, smem, X, (batch + X - 1) / X, p, s);
     }
-    static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), &c2c, nullptr, nullptr};
     }
 };
 
@@ -134,8 +135,8 @@ template <class PL, int X, int MINB> struct RealTileLaunchers {
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
         return launch_grid((const void *)k_c2r_tile<PL, X, MINB>, smem, X, (batch + X - 1) / X, p, s);
     }
-    static Variant make(const char *name, int priority, int priority_inv = -1) {
-        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 
