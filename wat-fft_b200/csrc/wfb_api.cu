@@ -86,13 +86,43 @@ cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long c
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// Per-launch tile counters of the persistent kernels: a ring of zero-initialised 64-bit slots per device.
+// A slot is re-zeroed on the launching stream right before the kernel that uses it; it would only be
+// reused while still live if 4096 persistent launches were outstanding across DIFFERENT streams.
+static cudaError_t next_counter(cudaStream_t s, unsigned long long **out) {
+    enum { RING = 4096 };
+    static std::map<int, unsigned long long *> rings;
+    static std::map<int, unsigned> heads;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    unsigned long long *ring;
+    unsigned idx;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = rings.find(dev);
+        if (it == rings.end()) {
+            unsigned long long *r = nullptr;
+            cudaError_t e = cudaMalloc(&r, RING * sizeof(unsigned long long));
+            if (e != cudaSuccess) return e;
+            it = rings.emplace(dev, r).first;
+            heads[dev] = 0;
+        }
+        ring = it->second;
+        idx = heads[dev]++ % RING;
+    }
+    *out = ring + idx;
+    return cudaMemsetAsync(*out, 0, sizeof(unsigned long long), s);
+}
+
 cudaError_t launch_persistent_raw(const void *kernel, size_t smem, int threads, long work_items, void *params, cudaStream_t s) {
     if (!kernel) return cudaErrorInvalidDeviceFunction;
     int resident;
     cudaError_t e = configure(kernel, smem, threads, &resident);
     if (e != cudaSuccess) return e;
+    StftParams sp = *static_cast<const StftParams *>(params);      // the only raw-parameter persistent kernel
+    if ((e = next_counter(s, &sp.ctr)) != cudaSuccess) return e;
     long grid = work_items < resident ? work_items : resident;
-    void *args[] = {params};
+    void *args[] = {&sp};
     e = cudaLaunchKernel(kernel, dim3((unsigned)grid), dim3(threads), args, smem, s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e != cudaSuccess ? e : cudaGetLastError();
@@ -104,8 +134,10 @@ cudaError_t launch_persistent(const void *kernel, size_t smem, int threads, long
     int resident;
     cudaError_t e = configure(kernel, smem, threads, &resident);
     if (e != cudaSuccess) return e;
+    KParams q = p;
+    if ((e = next_counter(s, &q.ctr)) != cudaSuccess) return e;
     long grid = work_items < resident ? work_items : resident;
-    void *args[] = {(void *)&p};
+    void *args[] = {&q};
     e = cudaLaunchKernel(kernel, dim3((unsigned)grid), dim3(threads), args, smem, s);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e != cudaSuccess ? e : cudaGetLastError();
@@ -429,6 +461,7 @@ static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void 
     p.rtw = pl->d_rtw[vi];
     p.batch = rows;
     p.scale = 1.0 / (double)pl->n;
+    p.ctr = nullptr;
     cudaError_t e;
     if (pl->kind == WFB_C2C)
         e = v.c2c(pl->layout == WFB_SPLIT ? IO_SPLIT : IO_INTERLEAVED, direction, p, rows, s);
@@ -647,6 +680,7 @@ int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void
     sp.tw = st->d_tw; sp.rtw = st->d_rtw;
     sp.frames = st->frames; sp.hop = st->hop; sp.wsize = st->wsize; sp.mode = st->mode & 0xFF;
     sp.db_floor = st->db_floor; sp.inv_range = st->inv_range; sp.inv_half_n = 2.0f / (float)st->fft_size;
+    sp.ctr = nullptr;
     // frames are TMA-copyable when their starts are 16-byte aligned (hop % 4 == 0, aligned base)
     static const int pipe_min = [] { const char *e = getenv("WFB_STFT_PIPE_MIN_N"); return e ? atoi(e) : 8192; }();
     const bool pipe = st->fft_size >= pipe_min && st->hop % 4 == 0 && st->wsize % 4 == 0 && ((uintptr_t)d_samples % 16) == 0;

@@ -356,6 +356,7 @@ struct KParams {
     const void *rtw;           // W_Nreal^k, k = 0..M, for the real transforms
     long batch;
     double scale;              // applied on store (1/N for the inverse c2c)
+    unsigned long long *ctr;   // persistent kernels: zeroed tile counter of this launch (dynamic tile claims)
 };
 
 enum IoMode { IO_SPLIT = 0, IO_INTERLEAVED = 1 };
@@ -777,6 +778,22 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Dynamic tile scheduling for the persistent kernels.  Tiles are claimed from a global counter, so they are
+// handed out in monotonic order and the CTAs of the whole GPU work on one tight, advancing window of the
+// arrays -- like the hardware CTA scheduler does for a one-tile-per-CTA launch.  A static `tile += gridDim.x`
+// schedule lets CTAs drift apart; tools/microbench/copy_pipe.cu measures 6.05 TB/s (static) vs 6.85 TB/s
+// (dynamic) for the same TMA-pipelined copy.  Called by warp 0; the claim for the NEXT tile is made when
+// its prefetch is issued, one iteration ahead, and published to the CTA through `slot[stage]`.
+template <class IssueFn>
+__device__ __forceinline__ void claim_and_issue(unsigned long long *ctr, long tiles, long *slot, int st, IssueFn &&issue) {
+    if (threadIdx.x < 32) {
+        long tn = 0;
+        if (threadIdx.x == 0) { tn = (long)atomicAdd(ctr, 1ULL); slot[st] = tn; }
+        tn = __shfl_sync(0xffffffffu, tn, 0);
+        if (tn < tiles) issue(tn, st);
+    }
+}
+
 template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr size_t pipe_buf_bytes() {
     size_t a = sizeof(cx<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
     return (a + 127) / 128 * 128;
@@ -839,16 +856,19 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
         }
     };
 
-    long tile = blockIdx.x;
-    if (tile < tiles) issue(tile, 0);
+    static_assert(PL::T * X >= 32, "tile claims are made by a full warp");
+    long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
+    claim_and_issue(p.ctr, tiles, slot, 0, issue);
     cx<R> x[PL::E];
     // (hoisting the last pass's thread-invariant twiddles into registers was tried and measured
     //  neutral at N = 4096 and 3-6 % slower below, from the extra 27 registers: profiles/r01_sweep.md)
-    for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
+    for (int it = 0;; it++) {
         const int st = it & 1;
         fence_proxy_async();      // our generic-proxy accesses to the other stage precede its refill
         __syncthreads();          // ... and everyone is done using it as scratch
-        if (tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        const long tile = slot[st];
+        if (tile >= tiles) break;
+        claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
         mbar_wait(mbar + st, (it >> 1) & 1);
 
         const long row = tile * ROWS + (long)xi * LANES;
@@ -979,15 +999,18 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
         }
     };
 
-    long tile = blockIdx.x;
-    if (tile < tiles) issue(tile, 0);
+    static_assert(PL::T * X >= 32, "tile claims are made by a full warp");
+    long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
+    claim_and_issue(p.ctr, tiles, slot, 0, issue);
     cx<R> x[PL::E];
     unsigned phasebits = 0;                            // mbarrier phase parity per stage (bit st)
-    for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
+    for (int it = 0;; it++) {
         const int st = it & 1;
         fence_proxy_async();
         __syncthreads();
-        if (tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        const long tile = slot[st];
+        if (tile >= tiles) break;
+        claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
         unsigned char *buf = smem_raw + st * BUF;
         if (tma_ok(tile)) {
             mbar_wait(mbar + st, (phasebits >> st) & 1u);
@@ -1264,6 +1287,7 @@ struct StftParams {
     float db_floor;            // gain - range
     float inv_range;           // 1 / range
     float inv_half_n;          // 1 / (N/2)
+    unsigned long long *ctr;   // pipelined kernel: zeroed tile counter of this launch
 };
 enum { STFT_MODE_DB = 0, STFT_MODE_COMPLEX = 1 };
 
@@ -1384,15 +1408,17 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
         }
     };
 
-    long tile = blockIdx.x;
-    if (tile < tiles) issue(tile, 0);
+    long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
+    claim_and_issue(sp.ctr, tiles, slot, 0, issue);
     cx<R> x[PL::E];
     const float2 *win = reinterpret_cast<const float2 *>(sp.window);
-    for (int it = 0; tile < tiles; tile += gridDim.x, it++) {
+    for (int it = 0;; it++) {
         const int st = it & 1;
         fence_proxy_async();
         __syncthreads();
-        if (tile + gridDim.x < tiles) issue(tile + gridDim.x, st ^ 1);
+        const long tile = slot[st];
+        if (tile >= tiles) break;
+        claim_and_issue(sp.ctr, tiles, slot, st ^ 1, issue);
         mbar_wait(mbar + st, (it >> 1) & 1);
         unsigned char *buf = smem_raw + st * BUF;
         const long frame = tile * X + xi;
