@@ -6,11 +6,13 @@ sm_100 device is present."""
 from __future__ import annotations
 
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libwatfft_b200.so"
+# WFB_LIB: A/B builds of the same library for tools/sweep.py (never a different implementation)
+LIB_PATH = Path(os.environ["WFB_LIB"]) if os.environ.get("WFB_LIB") else HERE / "libwatfft_b200.so"
 
 # enums of include/watfft_b200.h
 C2C, R2C = 0, 1

@@ -163,6 +163,7 @@ struct wfb_plan {
     int variant_inv;                   // inverse-direction kernel variant
     void *d_tw_fwd[8], *d_tw_inv[8];   // per variant
     void *d_rtw[8];                    // per variant (table format depends on the lane type)
+    std::vector<unsigned char> h_tw0_fwd[8], h_tw0_inv[8];   // head of each table for KParams::tw0 (scalar-lane variants)
     // buffers: C2C -> plane 0 / plane 1; R2C -> time / spectrum
     void *d_buf[2];
     void *h_buf[2];
@@ -285,6 +286,13 @@ static int upload_tables(wfb_plan *pl, int vi) {
         for (size_t i = 0; i + 1 < t.size(); i += 2) { o.push_back(t[i]); o.push_back(t[i]); o.push_back(t[i + 1]); o.push_back(t[i + 1]); }
         t.swap(o);
     };
+    if (v.lanes == 1) {
+        auto head = [](const std::vector<R> &t, std::vector<unsigned char> &h) {
+            h.assign(KParams::TW0_BYTES, 0);
+            memcpy(h.data(), t.data(), std::min<size_t>(t.size() * sizeof(R), KParams::TW0_BYTES));
+        };
+        head(fwd, pl->h_tw0_fwd[vi]); head(inv, pl->h_tw0_inv[vi]);
+    }
     widen(fwd); widen(inv);
     CK(cudaMalloc(&pl->d_tw_fwd[vi], fwd.size() * sizeof(R)));
     CK(cudaMalloc(&pl->d_tw_inv[vi], inv.size() * sizeof(R)));
@@ -462,6 +470,8 @@ static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void 
     p.batch = rows;
     p.scale = 1.0 / (double)pl->n;
     p.ctr = nullptr;
+    const std::vector<unsigned char> &h0 = direction == WFB_INVERSE ? pl->h_tw0_inv[vi] : pl->h_tw0_fwd[vi];
+    if (!h0.empty()) memcpy(p.tw0, h0.data(), KParams::TW0_BYTES);
     cudaError_t e;
     if (pl->kind == WFB_C2C)
         e = v.c2c(pl->layout == WFB_SPLIT ? IO_SPLIT : IO_INTERLEAVED, direction, p, rows, s);

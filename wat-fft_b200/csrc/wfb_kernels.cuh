@@ -143,6 +143,22 @@ __device__ __forceinline__ twd<f32x2> ld_tw(const float4 *p) {
     return {re, im, rneg(im)};
 }
 
+// Where a pass finds the twiddles that do not depend on the thread (pass 0: every group index is 0).
+// Entries below LIMIT come from a copy of the table's head inside the kernel parameter block: the values
+// reach the FFMA/FMUL instructions through the constant bank / uniform registers -- no LSU/MIO slot, no
+// scoreboard wait.  The rest (and everything for packed lanes, whose FFMA2 takes register pairs) comes from the
+// global stage table through the read-only data path (LDG.CONSTANT).  A radix-64 opening has 63 entries,
+// twice what the 63 uniform registers hold: measured, any constant share there is a loss (limit 0).
+template <typename R, int LIMIT> struct HTw {
+    const typename RT<R>::twel *c;     // parameter-block copy (unused when LIMIT == 0)
+    const typename RT<R>::twel *g;     // global table
+    template <int I> __device__ __forceinline__ twd<R> at() const {
+        if constexpr (I < LIMIT) { const typename RT<R>::twel t = c[I]; return {t.x, t.y, -t.y}; }
+        else return ld_tw(g + I);
+    }
+};
+template <typename R> using GTw = HTw<R, 0>;
+
 // shared-memory slot of logical element p (units of one complex value).  One pad slot per PADQ
 // elements keeps both the contiguous writes (tid + e*T) and the strided gathers of the later
 // passes (Rp*s'*j + t' + k*s') conflict-free; verified by tools/bank_sim.py for every plan.
@@ -186,6 +202,12 @@ template <class PL, int P> __host__ __device__ constexpr int out_elem(int slot) 
     return (slot % NB) + NB * slot_to_out(PL::code(P), slot / NB);
 }
 
+// inverse of out_elem: the register slot that holds logical element tid + e*T after pass P
+template <class PL, int P> __host__ __device__ constexpr int slot_of_elem(int e) {
+    for (int q = 0; q < PL::E; q++) if (out_elem<PL, P>(q) == e) return q;
+    return -1;
+}
+
 // First half of a twiddled radix-4 butterfly: t0 = A + w2*C, t1 = A - w2*C, t2 = w1*B + w3*D,
 // t3 = w1*B - w3*D  (fft_split_native_f32.wat:826-848).  Generic form: three products, four add/subs.
 template <typename R>
@@ -216,8 +238,8 @@ WFB_FUSED_R4(double)
 // ----------------------------------------------------------------------------------------
 // one fused pass over the E register-resident values of a thread
 // ----------------------------------------------------------------------------------------
-template <typename R, class PL, int P, bool INV>
-__device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, int tid) {
+template <typename R, class PL, int P, bool INV, class U>
+__device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, const U &tw0, int tid) {
     constexpr int CODE = PL::code(P);
     constexpr int RP = pass_rp(CODE);
     constexpr int NB = PL::E / RP;                 // register blocks per thread
@@ -243,7 +265,10 @@ __device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>
                 constexpr int c = hi_to_c(CODE, q, hi);
                 constexpr bool unit = (L_IN == 1 && c == 0);     // group 0: W^0 = 1
                 twd<R> w1, w2, w3;
-                if constexpr (!unit) {
+                if constexpr (!unit && L_IN == 1) {           // thread-independent: constant operands
+                    w1 = tw0.template at<off + c>();
+                    if constexpr (r == 4) { w2 = tw0.template at<off + lq + c>(); w3 = tw0.template at<off + 2 * lq + c>(); }
+                } else if constexpr (!unit) {
                     w1 = ld_tw(twj + (off + L_IN * c));
                     if constexpr (r == 4) {
                         w2 = ld_tw(twj + (off + lq + L_IN * c));
@@ -333,16 +358,16 @@ __device__ __forceinline__ void fill_inputs(cx<R> (&x)[PL::E], const cx<R> *sm, 
 
 // all passes; on entry x holds pass 0's inputs (element tid + e*T in slot e), on exit the last
 // pass's outputs.  `smem_dirty`: other threads may still be reading smem when we get here.
-template <typename R, class PL, int PADQ, int X, bool INV, int P = 0>
-__device__ __forceinline__ void run_all(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, cx<R> *sm,
+template <typename R, class PL, int PADQ, int X, bool INV, int P = 0, class U>
+__device__ __forceinline__ void run_all(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, const U &tw0, cx<R> *sm,
                                         int tid, int xi, bool smem_dirty) {
-    run_pass<R, PL, P, INV>(x, tw, tid);
+    run_pass<R, PL, P, INV>(x, tw, tw0, tid);
     if constexpr (P + 1 < PL::npass()) {
         if (smem_dirty || P > 0) sync_transform<PL::T, X>(xi);
         spill_outputs<R, PL, P, PADQ>(x, sm, tid);
         sync_transform<PL::T, X>(xi);
         fill_inputs<R, PL, P + 1, PADQ>(x, sm, tid);
-        run_all<R, PL, PADQ, X, INV, P + 1>(x, tw, sm, tid, xi, true);
+        run_all<R, PL, PADQ, X, INV, P + 1>(x, tw, tw0, sm, tid, xi, true);
     }
 }
 
@@ -357,6 +382,22 @@ struct KParams {
     long batch;
     double scale;              // applied on store (1/N for the inverse c2c)
     unsigned long long *ctr;   // persistent kernels: zeroed tile counter of this launch (dynamic tile claims)
+    // the first TW0_BYTES of the stage table `tw` (scalar-lane variants): pass 0's thread-independent twiddles,
+    // read as constant-bank operands (see CTw)
+    enum { TW0_BYTES = 1008 };                         // 63 entries of a radix-64 opening pass in f64
+    alignas(16) unsigned char tw0[TW0_BYTES];
+};
+#ifndef WFB_CTW_LIMIT64
+#define WFB_CTW_LIMIT64 0
+#endif
+// pass-0 twiddle source of a kernel with lane type R and plan PL
+template <typename R, class PL> struct UTw {
+    static constexpr int ENTRIES = PL::tw_off(1, 0);   // table entries of pass 0
+    static constexpr int LIMIT = RT<R>::LANES != 1 ? 0 : (ENTRIES <= 31 ? ENTRIES : WFB_CTW_LIMIT64);
+    static_assert(LIMIT * sizeof(typename RT<R>::twel) <= KParams::TW0_BYTES, "tw0 capacity");
+    static __device__ __forceinline__ HTw<R, LIMIT> make(const KParams &p, const typename RT<R>::twel *tw) {
+        return {reinterpret_cast<const typename RT<R>::twel *>(p.tw0), tw};
+    }
 };
 
 enum IoMode { IO_SPLIT = 0, IO_INTERLEAVED = 1 };
@@ -425,7 +466,7 @@ template <typename R, int T, int X> struct Rows {
 // Transform 1 and 3 (f32) / 4 (f64): batched c2c, split or interleaved I/O
 // ----------------------------------------------------------------------------------------
 template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB>
-__global__ void __launch_bounds__(PL::T *X, MINB) k_c2c(KParams p) {
+__global__ void __launch_bounds__(PL::T *X, MINB) k_c2c(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using S = typename VecOf<R>::s;
@@ -451,7 +492,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c(KParams p) {
         static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = mk<R>(RT<R>::splat(0), RT<R>::splat(0)); });
     }
 
-    run_all<R, PL, PADQ, X, INV>(x, tw, sm, tid, g.xi, false);
+    run_all<R, PL, PADQ, X, INV>(x, tw, UTw<R, PL>::make(p, tw), sm, tid, g.xi, false);
 
     if (g.active) {
         const R sc = RT<R>::splat((S)p.scale);
@@ -524,7 +565,7 @@ template <> struct RealPost<double> {
 };
 
 template <typename R, class PL, int X, int PADQ, int MINB>
-__global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(KParams p) {
+__global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using V2 = typename VecOf<R>::v2;
@@ -544,7 +585,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(KParams p) {
         static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = mk<R>(RT<R>::splat(0), RT<R>::splat(0)); });
     }
 
-    run_all<R, PL, PADQ, X, false>(x, tw, sm, tid, g.xi, false);
+    run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), sm, tid, g.xi, false);
 
     // Z -> shared memory in natural order
     if (PL::npass() > 1) sync_transform<PL::T, X>(g.xi);
@@ -586,7 +627,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(KParams p) {
 // formulas in double.
 // ----------------------------------------------------------------------------------------
 template <typename R, class PL, int X, int PADQ, int MINB>
-__global__ void __launch_bounds__(PL::T *X, MINB) k_c2r(KParams p) {
+__global__ void __launch_bounds__(PL::T *X, MINB) k_c2r(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using S = typename VecOf<R>::s;
@@ -633,7 +674,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2r(KParams p) {
         static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = base[pad_off<PADQ>(e * PL::T)]; });
     }
 
-    run_all<R, PL, PADQ, X, true>(x, tw, sm, tid, g.xi, true);
+    run_all<R, PL, PADQ, X, true>(x, tw, UTw<R, PL>::make(p, tw), sm, tid, g.xi, true);
 
     if (g.active) {
         V2 *z = reinterpret_cast<V2 *>(p.out0) + g.row * M + tid;
@@ -655,7 +696,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2r(KParams p) {
 // per-row LDS.128/STS.128 of 8 consecutive threads then fall in 8 distinct 16-byte bank groups.
 // ----------------------------------------------------------------------------------------
 template <typename R, class PL, int X, int IO, bool INV, int MINB>
-__global__ void __launch_bounds__(X, MINB) k_c2c_tile(KParams p) {
+__global__ void __launch_bounds__(X, MINB) k_c2c_tile(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && RT<R>::LANES == 1, "tile kernel: one thread per row");
     static_assert(sizeof(R) == 4, "tile kernel is f32");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -702,7 +743,7 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tile(KParams p) {
         x[2 * h] = mk<R>(v.x, v.y);
         x[2 * h + 1] = mk<R>(v.z, v.w);
     });
-    run_pass<R, PL, 0, INV>(x, tw, 0);
+    run_pass<R, PL, 0, INV>(x, tw, UTw<R, PL>::make(p, tw), 0);
     {
         const float sc = (float)p.scale;
         // register slot s holds element out_elem(s); emit adjacent element pairs as one STS.128
@@ -800,7 +841,7 @@ template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr s
 }
 
 template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, bool RC = false>
-__global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
+__global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using S = typename VecOf<R>::s;
@@ -905,7 +946,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(KParams p) {
         // have its inputs in registers before any group spills
         if constexpr (PL::npass() > 1) __syncthreads();
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(N);
-        run_all<R, PL, PADQ, X, INV>(x, tw, scratch, tid, xi, false);
+        run_all<R, PL, PADQ, X, INV>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
 
         if (active) {
             const long rs = two ? N : 0;
@@ -951,7 +992,7 @@ template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ c
 }
 
 template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false>
-__global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
+__global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
     static_assert(!C2R || X % 2 == 0, "c2r tiles need an even number of rows (16-byte alignment)");
     static_assert(!RC || (!C2R && PL::N >= 32 && PL::T * X >= 32), "row copies: r2c only (c2r rows are 8-byte aligned)");
@@ -1030,76 +1071,78 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
             // ---------------- r2c
             static_for<PL::E>([&](auto E_) { CIDX(e, E_); const V2 a = raw[tid + e * PL::T]; x[e] = mk<R>(a.x, a.y); });
             __syncthreads();                           // dense tile and padded scratch alias
-            run_all<R, PL, PADQ, X, false>(x, tw, scratch, tid, xi, false);
+            run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
             if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
-            spill_outputs<R, PL, LAST, PADQ>(x, scratch, tid);
+            // Hermitian post-process: bin k = tid + i*T (k < M/2) pairs the thread's OWN register value Z[k] with
+            // Z[M-k], which another thread of the group owns.  Only the upper half (elements >= M/2) travels
+            // through shared memory: half a spill and half a re-read instead of a full spill and two full reads.
+            // Z[k'] is parked at UNPADDED index M - k' (1..M/2), i.e. at the bin index of the thread that reads it:
+            // readers tid, tid+1, ... hit consecutive words, and so do writers (thread 0 lands on column T of the
+            // row the others fill at columns 1..T-1).
+            static_for<PL::E>([&](auto S_) {
+                CIDX(slot, S_);
+                constexpr int e = out_elem<PL, LAST>(slot);
+                if constexpr (e >= PL::E / 2) scratch[M - e * PL::T - tid] = x[slot];
+            });
             sync_transform<PL::T, X>(xi);
             if (active) {
                 V2 *out = reinterpret_cast<V2 *>(p.out0) + row * (M + 1);
                 constexpr int HALF = M / 2;
-                constexpr int PER = (HALF + PL::T - 1) / PL::T;
+                constexpr int PER = PL::E / 2;
+                static_assert(PER * PL::T == HALF, "bins per thread");
                 const R zero = RT<R>::splat(0);
                 static_for<PER>([&](auto I_) {
                     CIDX(i, I_);
                     const int k = tid + i * PL::T;
-                    if (k < HALF) {
-                        if (i == 0 && k == 0) {
-                            const cx<R> z0 = scratch[0];
-                            GIO<R>::st_il(out, 0, false, mk<R>(radd(z0.x, z0.y), zero));
-                            GIO<R>::st_il(out + M, 0, false, mk<R>(rsub(z0.x, z0.y), zero));
-                            const cx<R> zh = scratch[pad_idx<PADQ>(HALF)];
-                            GIO<R>::st_il(out + HALF, 0, false, RealPost<R>::middle(zh, ld_tw(rtw + HALF), M));
-                        } else {
-                            const cx<R> z = scratch[pad_idx<PADQ>(k)], zm = scratch[pad_idx<PADQ>(M - k)];
-                            cx<R> xk, xm;
-                            RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);
-                            GIO<R>::st_il(out + k, 0, false, xk);
-                            GIO<R>::st_il(out + (M - k), 0, false, xm);
-                        }
+                    const cx<R> z = x[slot_of_elem<PL, LAST>(i)];
+                    if (i == 0 && k == 0) {
+                        GIO<R>::st_il(out, 0, false, mk<R>(radd(z.x, z.y), zero));
+                        GIO<R>::st_il(out + M, 0, false, mk<R>(rsub(z.x, z.y), zero));
+                        const cx<R> zh = scratch[HALF];
+                        GIO<R>::st_il(out + HALF, 0, false, RealPost<R>::middle(zh, ld_tw(rtw + HALF), M));
+                    } else {
+                        const cx<R> zm = scratch[k];
+                        cx<R> xk, xm;
+                        RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);
+                        GIO<R>::st_il(out + k, 0, false, xk);
+                        GIO<R>::st_il(out + (M - k), 0, false, xm);
                     }
                 });
             }
         } else {
             // ---------------- c2r: Hermitian pre-process into registers, then through the scratch
             constexpr int HALF = M / 2;
-            constexpr int PER = (HALF + PL::T - 1) / PL::T;
-            static_assert(2 * PER <= PL::E, "pre-process registers");
+            constexpr int PER = PL::E / 2;
+            static_assert(PER * PL::T == HALF, "bins per thread");
+            // Z[k] for k = tid + i*T < M/2 is this thread's own pass-0 input e = i: it stays in its register.
+            // Only the mirrored halves Z[M-k] travel through the scratch to the threads that own them.
             const R sc = RT<R>::splat(S(0.5) / S(M));
-            cx<R> z0 = mk<R>(RT<R>::splat(0), RT<R>::splat(0));
+            cx<R> zb[PER];
             static_for<PER>([&](auto I_) {
                 CIDX(i, I_);
                 const int k = tid + i * PL::T;
-                if (k < HALF) {
-                    if (i == 0 && k == 0) {
-                        const V2 a0 = raw[0], am = raw[M];          // real parts only (:1679-1684)
-                        z0 = mk<R>(rmul(radd(a0.x, am.x), sc), rmul(rsub(a0.x, am.x), sc));
-                    }
-                    const int kk = (k == 0) ? HALF : k;
-                    const V2 a = raw[kk], b = raw[M - kk];
-                    const twd<R> w = ld_tw(rtw + kk);
-                    const R gr = radd(a.x, b.x), gi = rsub(a.y, b.y), ur = rsub(a.x, b.x), ui = radd(a.y, b.y);
-                    const R hr = rfma(w.y, ui, rmul(w.x, ur)), hi = rfma(w.ny, ur, rmul(w.x, ui));
-                    x[2 * i] = mk<R>(rmul(sc, rsub(gr, hi)), rmul(sc, radd(gi, hr)));
-                    x[2 * i + 1] = mk<R>(rmul(sc, radd(gr, hi)), rmul(sc, rsub(hr, gi)));
+                const int kk = (i == 0 && k == 0) ? HALF : k;
+                const V2 a = raw[kk], b = raw[M - kk];
+                const twd<R> w = ld_tw(rtw + kk);
+                const R gr = radd(a.x, b.x), gi = rsub(a.y, b.y), ur = rsub(a.x, b.x), ui = radd(a.y, b.y);
+                const R hr = rfma(w.y, ui, rmul(w.x, ur)), hi = rfma(w.ny, ur, rmul(w.x, ui));
+                x[i] = mk<R>(rmul(sc, rsub(gr, hi)), rmul(sc, radd(gi, hr)));
+                zb[i] = mk<R>(rmul(sc, radd(gr, hi)), rmul(sc, rsub(hr, gi)));
+                if (i == 0 && k == 0) {
+                    const V2 a0 = raw[0], am = raw[M];              // real parts only (:1679-1684)
+                    x[0] = mk<R>(rmul(radd(a0.x, am.x), sc), rmul(rsub(a0.x, am.x), sc));
                 }
             });
             __syncthreads();                           // every group has consumed its raw rows
             static_for<PER>([&](auto I_) {
                 CIDX(i, I_);
                 const int k = tid + i * PL::T;
-                if (k < HALF) {
-                    if (i == 0 && k == 0) scratch[0] = z0;
-                    const int kk = (k == 0) ? HALF : k;
-                    scratch[pad_idx<PADQ>(kk)] = x[2 * i];          // forward first, mirrored second (:1722-1740)
-                    scratch[pad_idx<PADQ>(M - kk)] = x[2 * i + 1];
-                }
+                const int kk = (i == 0 && k == 0) ? HALF : k;       // Z[M/2]: the mirrored form survives (:1722-1740)
+                scratch[kk] = zb[i];                   // Z[M - kk] parked at unpadded index kk (conflict-free both ways)
             });
             sync_transform<PL::T, X>(xi);
-            {
-                const cx<R> *base = scratch + pad_idx<PADQ>(tid);
-                static_for<PL::E>([&](auto E_) { CIDX(e, E_); x[e] = base[pad_off<PADQ>(e * PL::T)]; });
-            }
-            run_all<R, PL, PADQ, X, true>(x, tw, scratch, tid, xi, true);
+            static_for<PER>([&](auto E_) { CIDX(e, E_); x[PER + e] = scratch[M - (PER + e) * PL::T - tid]; });
+            run_all<R, PL, PADQ, X, true>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, true);
             if (active) {
                 V2 *z = reinterpret_cast<V2 *>(p.out0) + row * M + tid;
                 static_for<PL::E>([&](auto S_) {
@@ -1120,13 +1163,9 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(KParams p) {
 // 8-byte words, so the dense [rows][M+1] tile is already bank-conflict-free for per-thread row
 // access and is copied to/from global memory as one contiguous, 16-byte aligned block.
 // ----------------------------------------------------------------------------------------
-template <class PL, int P> __host__ __device__ constexpr int slot_of_elem(int e) {
-    for (int q = 0; q < PL::E; q++) if (out_elem<PL, P>(q) == e) return q;
-    return -1;
-}
 
 template <class PL, int X, int MINB>
-__global__ void __launch_bounds__(X, MINB) k_r2c_tile(KParams p) {
+__global__ void __launch_bounds__(X, MINB) k_r2c_tile(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 2 == 0, "tile kernel: one thread per row");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using R = float;
@@ -1161,7 +1200,7 @@ __global__ void __launch_bounds__(X, MINB) k_r2c_tile(KParams p) {
             x[2 * h + 1] = mk<R>(v.z, v.w);
         });
     }
-    run_pass<R, PL, 0, false>(x, tw, 0);
+    run_pass<R, PL, 0, false>(x, tw, UTw<R, PL>::make(p, tw), 0);
     __syncthreads();                                   // input rows and output rows alias
 
     {   // Hermitian post-process in registers -> dense output row t ((M+1) float2, odd stride)
@@ -1197,7 +1236,7 @@ __global__ void __launch_bounds__(X, MINB) k_r2c_tile(KParams p) {
 }
 
 template <class PL, int X, int MINB>
-__global__ void __launch_bounds__(X, MINB) k_c2r_tile(KParams p) {
+__global__ void __launch_bounds__(X, MINB) k_c2r_tile(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 2 == 0, "tile kernel: one thread per row");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using R = float;
@@ -1240,7 +1279,7 @@ __global__ void __launch_bounds__(X, MINB) k_c2r_tile(KParams p) {
             x[M - k] = mk<R>(sc * (gr + hi), sc * (hr - gi));
         });
     }
-    run_pass<R, PL, 0, true>(x, tw, 0);
+    run_pass<R, PL, 0, true>(x, tw, UTw<R, PL>::make(p, tw), 0);
     __syncthreads();                                   // input rows and output rows alias
 
     {   // time-domain row: z[j] = (x[2j], x[2j+1]); adjacent complex pairs as one STS.128
@@ -1335,7 +1374,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
             x[e] = mk<R>(a, b);
         });
     }
-    run_all<R, PL, PADQ, X, false>(x, tw, sm, tid, xi, false);
+    run_all<R, PL, PADQ, X, false>(x, tw, GTw<R>{nullptr, tw}, sm, tid, xi, false);
     if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
     spill_outputs<R, PL, LAST, PADQ>(x, sm, tid);
     sync_transform<PL::T, X>(xi);
@@ -1437,7 +1476,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
             x[e] = mk<R>(a, b);
         });
         __syncthreads();                               // raw rows and padded scratch alias
-        run_all<R, PL, PADQ, X, false>(x, tw, scratch, tid, xi, false);
+        run_all<R, PL, PADQ, X, false>(x, tw, GTw<R>{nullptr, tw}, scratch, tid, xi, false);
         if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
         spill_outputs<R, PL, LAST, PADQ>(x, scratch, tid);
         sync_transform<PL::T, X>(xi);

@@ -96,14 +96,14 @@ template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ>
 };
 
 // persistent TMA-pipelined r2c / c2r (scalar lanes)
-template <typename R, class PL, int X, int MINB, bool RC = false> struct RealPipeLaunchers {
-    static constexpr size_t smem_f = 2 * real_pipe_buf_bytes<R, PL, PADQ, X, false>() + 64;
-    static constexpr size_t smem_i = 2 * real_pipe_buf_bytes<R, PL, PADQ, X, true>() + 64;
+template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ> struct RealPipeLaunchers {
+    static constexpr size_t smem_f = 2 * real_pipe_buf_bytes<R, PL, PQ, X, false>() + 64;
+    static constexpr size_t smem_i = 2 * real_pipe_buf_bytes<R, PL, PQ, X, true>() + 64;
     static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_persistent((const void *)k_real_pipe<R, PL, X, PADQ, false, MINB, RC>, smem_f, PL::T * X, (batch + X - 1) / X, p, s);
+        return launch_persistent((const void *)k_real_pipe<R, PL, X, PQ, false, MINB, RC>, smem_f, PL::T * X, (batch + X - 1) / X, p, s);
     }
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_persistent((const void *)k_real_pipe<R, PL, X, PADQ, true, MINB>, smem_i, PL::T * X, (batch + X - 1) / X, p, s);
+        return launch_persistent((const void *)k_real_pipe<R, PL, X, PQ, true, MINB>, smem_i, PL::T * X, (batch + X - 1) / X, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
         return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
@@ -182,6 +182,10 @@ using P32_2048_T64 = Plan<2048, 64, 0x24, 0x44, 0x44>;
 using P64_4096 = Plan<4096, 64, 0x444, 0x444>;
 using P64_2048 = Plan<2048, 32, 0x244, 0x444>;
 using P64_1024 = Plan<1024, 16, 0x44, 0x444>;
+// 32 values per thread: two passes, one exchange; a 1024-point transform is ONE warp (no block barriers).
+// f32 only (tolerance-based parity lets the stage radices be regrouped as 2,4,4 | 2,4,4).
+using P32_1024 = Plan<1024, 32, 0x244, 0x244>;    // pad slot per 32 values
+using P32_512 = Plan<512, 16, 0x244, 0x44>;
 // thread-per-row plans for the tile kernels (whole transform in registers)
 using T32_32 = Plan<32, 1, 0x244>;
 using T32_64 = Plan<64, 1, 0x444>;

@@ -4,6 +4,7 @@ namespace wfb {
 #define VP(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB>::make(#PL "_pipe" #X, PRIO)
 #define VPR(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, true>::make(#PL "_pipe" #X "_rc", PRIO)
 #define VP64(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, false, 64>::make(#PL "_pipe" #X, PRIO)
+#define VP32(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, false, 32>::make(#PL "_pipe" #X, PRIO)
 #define VP2(PL, X, MINB, PRIO) PipeLaunchers<f32x2, PL, X, MINB>::make(#PL "_pipe" #X "_x2", PRIO)
 const std::vector<Variant> &variants_f32_pipe() {
     // 16 KB tiles are the sweet spot for the dynamically scheduled pipeline (8 KB and 32 KB tiles lose 10-30 %).
@@ -13,6 +14,8 @@ const std::vector<Variant> &variants_f32_pipe() {
         VPR(F32_128, 16, 2, 34),
         VP(F32_256, 8, 2, 36), VP(F32_256, 16, 2, 30), VP2(F32_256, 8, 2, 33),
         VP(F32_512, 4, 2, 34), VP2(F32_512, 4, 2, 30),
+        // 32 values per thread, one exchange: equal at burst clocks, 7-11 % faster power-capped (fewer instructions)
+        VP(P32_512, 4, 2, 35), VP32(P32_1024, 2, 2, 34),
         VP(F32_1024, 2, 2, 33),
         VP(F32_2048, 1, 4, 30),
         VP(F32_4096, 1, 2, 30), VP(F32_8192, 1, 1, 30),

@@ -2,11 +2,16 @@
 #include "wfb_registry.h"
 namespace wfb {
 #define VR(PL, X, MINB, ...) RealPipeLaunchers<float, PL, X, MINB>::make(#PL "_rpipe" #X, __VA_ARGS__)
+#define VRQ(PL, X, MINB, PQ, ...) RealPipeLaunchers<float, PL, X, MINB, false, PQ>::make(#PL "_rpipe" #X, __VA_ARGS__)
 #define VRC(PL, X, MINB, ...) RealPipeLaunchers<float, PL, X, MINB, true>::make(#PL "_rpipe" #X "_rc", __VA_ARGS__)
 const std::vector<Variant> &variants_f32_real_pipe() {
     static const std::vector<Variant> v = {
         VR(F32_64, 32, 2, 30), VR(F32_128, 16, 2, 9, 30), VR(F32_256, 8, 2, 30), VR(F32_512, 4, 2, 30),
         VRC(F32_64, 32, 2, 31, 8), VRC(F32_128, 16, 2, 31, 8), VRC(F32_256, 16, 2, 29, 8),
+        // one-exchange plans (32 / 64 values per thread): the real kernels are shared-memory-pipe bound at M >= 512,
+        // so dropping an exchange buys 5-20 % there (it buys nothing for c2c at the same M)
+        VRQ(P32_512, 4, 2, 16, 31), VRQ(P32_1024, 2, 2, 32, 31), VRQ(P32_1024, 4, 2, 32, 27),
+        VRQ(P64_2048, 2, 1, 64, 31), VRQ(P64_4096, 2, 1, 64, 28),
         VR(F32_1024, 2, 2, 30), VR(F32_2048, 2, 2, 30, 9), VR(F32_4096, 2, 1, 30),
     };
     return v;
