@@ -818,6 +818,13 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// smem -> global bulk copy (TMA store), tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's committed bulk stores have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // Dynamic tile scheduling for the persistent kernels.  Tiles are claimed from a global counter, so they are
 // handed out in monotonic order and the CTAs of the whole GPU work on one tight, advancing window of the
@@ -973,6 +980,151 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
             }
         }
     }
+}
+
+
+// ----------------------------------------------------------------------------------------
+// Persistent, fully TMA-fed thread-per-row c2c (N <= 64, f32).  Same arithmetic as k_c2c_tile, but no thread
+// ever touches global memory: rows arrive by bulk copy, are transformed in place by their thread, and leave by
+// bulk store.  Against k_c2c_tile this drops the cooperative staging loops -- a third of the LSU instructions
+// and half the shared-memory traffic per row, which is what the kernel is short of once the SM clock sits at
+// the power cap.
+//   * The copy engine retires roughly one bulk operation per 14 clocks per SM (measured: 256-byte row copies
+//     cap the kernel at 78 % of the HBM peak, 512-byte ones do not), so G consecutive rows travel as ONE
+//     512-byte copy per plane.  A group lands as [G rows re | G rows im | 16 bytes pad] (interleaved: [G rows |
+//     pad]); thread t owns row G*(t mod X/G) + t/(X/G) of the tile, so 8 consecutive lanes sit in 8 consecutive
+//     groups, whose stride is an odd number of 16-byte bank groups: LDS.128/STS.128 are conflict-free.
+//   * Two stages; the stage being refilled is the one whose bulk stores were issued last, so the issuing lanes
+//     drain their own store group (cp.async.bulk.wait_group.read) right before the refill -- after the row
+//     loads of the current tile, which gives the store engine that time for free.
+// ----------------------------------------------------------------------------------------
+template <class PL, int IO> __host__ __device__ constexpr int tpipe_group() {
+    const int row_bytes = (IO == IO_SPLIT ? 4 : 8) * PL::N;           // bytes of one row in one plane
+    return row_bytes >= 512 ? 1 : 512 / row_bytes;
+}
+template <class PL, int X, int IO> __host__ __device__ constexpr size_t tpipe_buf_bytes() {
+    constexpr int G = tpipe_group<PL, IO>();
+    return ((size_t)(G * 8 * PL::N + 16) * (X / G) + 127) / 128 * 128;
+}
+
+template <class PL, int X, int IO, bool INV, int MINB>
+__global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ KParams p) {
+    static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 32 == 0, "tile kernel: one thread per row, whole warps");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using R = float;
+    constexpr int N = PL::N;
+    constexpr int G = tpipe_group<PL, IO>();           // rows per bulk copy
+    constexpr int NG = X / G;                          // groups per tile
+    static_assert(X % G == 0 && NG % 8 == 0, "8 consecutive lanes must sit in 8 consecutive groups");
+    constexpr int GSTR = G * 8 * N + 16;               // group stride, bytes (odd multiple of 16)
+    constexpr int PLANE = (IO == IO_SPLIT ? 4 : 8) * N; // bytes of one row in one plane
+    constexpr size_t BUF = tpipe_buf_bytes<PL, X, IO>();
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
+    long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);
+    const int t = threadIdx.x;
+    const int gj = t % NG, gb = t / NG;                // my group, my row within it
+    const long tiles = (p.batch + X - 1) / X;
+    const float2 *tw = reinterpret_cast<const float2 *>(p.tw);
+    auto cta_sync = [&]() { if constexpr (X == 32) __syncwarp(); else __syncthreads(); };
+
+    if (t == 0) {
+        mbar_init(mbar + 0, 1);
+        mbar_init(mbar + 1, 1);
+        fence_proxy_async();
+    }
+    cta_sync();
+
+    auto tile_rows = [&](long tile) { const long row = tile * X; return (p.batch - row < X) ? (int)(p.batch - row) : X; };
+    auto issue = [&](long tile, int st) {              // warp 0, all lanes
+        const int rows = tile_rows(tile);
+        unsigned char *buf = smem_raw + st * BUF;
+        bulk_wait_read_all();                          // this lane's stores out of this stage have left shared memory
+        if (t == 0) mbar_expect_tx(mbar + st, (uint32_t)(rows * 8 * N));
+        __syncwarp();
+        for (int g = t; g * G < rows; g += 32) {
+            const long row = tile * X + (long)g * G;
+            const int nr = rows - g * G < G ? rows - g * G : G;
+            unsigned char *dst = buf + (size_t)g * GSTR;
+            if constexpr (IO == IO_SPLIT) {
+                tma_load_1d(dst, reinterpret_cast<const float *>(p.in0) + row * N, (uint32_t)(nr * PLANE), mbar + st);
+                tma_load_1d(dst + G * PLANE, reinterpret_cast<const float *>(p.in1) + row * N, (uint32_t)(nr * PLANE), mbar + st);
+            } else {
+                tma_load_1d(dst, reinterpret_cast<const float *>(p.in0) + row * 2 * N, (uint32_t)(nr * PLANE), mbar + st);
+            }
+        }
+    };
+
+    claim_and_issue(p.ctr, tiles, slot, 0, issue);
+    unsigned phasebits = 0;
+    cx<R> x[N];
+    for (int it = 0;; it++) {
+        const int st = it & 1;
+        cta_sync();                                    // slot[st] is published; last iteration's stores are issued
+        const long tile = slot[st];
+        if (tile >= tiles) break;
+        unsigned char *buf = smem_raw + st * BUF;
+        const int rows = tile_rows(tile);
+        mbar_wait(mbar + st, (phasebits >> st) & 1u);
+        phasebits ^= 1u << st;
+
+        unsigned char *grp = buf + (size_t)gj * GSTR;
+        float4 *rowp = reinterpret_cast<float4 *>(grp + gb * PLANE);               // re row (or the interleaved row)
+        float4 *rowq = reinterpret_cast<float4 *>(grp + (G + gb) * PLANE);         // im row (split only)
+        if constexpr (IO == IO_SPLIT) {
+            static_for<N / 4>([&](auto H_) {
+                CIDX(h, H_);
+                const float4 a = rowp[h], b = rowq[h];
+                x[4 * h] = mk<R>(a.x, b.x); x[4 * h + 1] = mk<R>(a.y, b.y);
+                x[4 * h + 2] = mk<R>(a.z, b.z); x[4 * h + 3] = mk<R>(a.w, b.w);
+            });
+        } else {
+            static_for<N / 2>([&](auto H_) {
+                CIDX(h, H_);
+                const float4 v = rowp[h];
+                x[2 * h] = mk<R>(v.x, v.y); x[2 * h + 1] = mk<R>(v.z, v.w);
+            });
+        }
+        claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);       // refill the other stage while this tile computes
+
+        run_pass<R, PL, 0, INV>(x, tw, UTw<R, PL>::make(p, tw), 0);
+
+        const float sc = INV ? (float)p.scale : 1.0f;
+        if constexpr (IO == IO_SPLIT) {
+            static_for<N / 4>([&](auto H_) {
+                CIDX(h, H_);
+                constexpr int s0 = slot_of_elem<PL, 0>(4 * h), s1 = slot_of_elem<PL, 0>(4 * h + 1);
+                constexpr int s2 = slot_of_elem<PL, 0>(4 * h + 2), s3 = slot_of_elem<PL, 0>(4 * h + 3);
+                float4 a = make_float4(x[s0].x, x[s1].x, x[s2].x, x[s3].x), b = make_float4(x[s0].y, x[s1].y, x[s2].y, x[s3].y);
+                if (INV) { a = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc); b = make_float4(b.x * sc, b.y * sc, b.z * sc, b.w * sc); }
+                rowp[h] = a; rowq[h] = b;
+            });
+        } else {
+            static_for<N / 2>([&](auto H_) {
+                CIDX(h, H_);
+                constexpr int s0 = slot_of_elem<PL, 0>(2 * h), s1 = slot_of_elem<PL, 0>(2 * h + 1);
+                float4 v = make_float4(x[s0].x, x[s0].y, x[s1].x, x[s1].y);
+                if (INV) v = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+                rowp[h] = v;
+            });
+        }
+        fence_proxy_async();                           // generic-proxy writes -> visible to the bulk-copy engine
+        cta_sync();
+        if (t < 32) {
+            for (int g = t; g * G < rows; g += 32) {
+                const long row = tile * X + (long)g * G;
+                const int nr = rows - g * G < G ? rows - g * G : G;
+                const unsigned char *src = buf + (size_t)g * GSTR;
+                if constexpr (IO == IO_SPLIT) {
+                    tma_store_1d(reinterpret_cast<float *>(p.out0) + row * N, src, (uint32_t)(nr * PLANE));
+                    tma_store_1d(reinterpret_cast<float *>(p.out1) + row * N, src + G * PLANE, (uint32_t)(nr * PLANE));
+                } else {
+                    tma_store_1d(reinterpret_cast<float *>(p.out0) + row * 2 * N, src, (uint32_t)(nr * PLANE));
+                }
+            }
+            bulk_commit();
+        }
+    }
+    if (t < 32) bulk_wait_read_all();                  // shared memory must outlive the stores that read it
 }
 
 
@@ -1304,6 +1456,170 @@ __global__ void __launch_bounds__(X, MINB) k_c2r_tile(const __grid_constant__ KP
             if (r < rows) st_stream(dst + f, *reinterpret_cast<const float4 *>(smf + r * RSO + 4 * c));
         }
     }
+}
+
+
+// ----------------------------------------------------------------------------------------
+// Persistent, fully TMA-fed thread-per-row r2c / c2r (N = 64, 128; core M = N/2), the real counterparts of
+// k_c2c_tpipe.  The time-domain side uses the grouped, padded rows of k_c2c_tpipe (512-byte bulk copies); the
+// spectrum side is the dense [rows][M+1] tile of k_r2c_tile, which is one contiguous block in global memory and
+// moves as ONE bulk copy.  Both sides live in the same stage buffer (the thread owns its row in registers in
+// between).  Thread <-> row: within every 8G lanes, row = base + G*(lane % 8) + lane / 8, so 8 consecutive lanes
+// sit in 8 consecutive groups (LDS.128 on the padded side) and 16 consecutive lanes cover 16 consecutive rows
+// (LDS.64 on the dense side, odd row stride): both sides are conflict-free.  A ragged last tile (fewer than X
+// rows) moves its spectrum rows with plain loads/stores (bulk copies need 16-byte sizes).
+// ----------------------------------------------------------------------------------------
+template <class PL> __host__ __device__ constexpr int rtpipe_group() { return 8 * PL::N >= 512 ? 1 : 512 / (8 * PL::N); }
+template <class PL, int X> __host__ __device__ constexpr size_t rtpipe_buf_bytes() {
+    constexpr int G = rtpipe_group<PL>();
+    size_t padded = (size_t)(G * 8 * PL::N + 16) * (X / G), dense = (size_t)X * (PL::N + 1) * 8;
+    return ((padded > dense ? padded : dense) + 127) / 128 * 128;
+}
+
+template <class PL, int X, bool C2R, int MINB>
+__global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ KParams p) {
+    static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 32 == 0, "tile kernel: one thread per row, whole warps");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using R = float;
+    constexpr int M = PL::N, N = 2 * M, HALF = M / 2;
+    constexpr int G = rtpipe_group<PL>();              // time-domain rows per bulk copy
+    static_assert(G <= 2 && X % (8 * G) == 0, "thread <-> row mapping covers G = 1, 2");
+    constexpr int ROWT = 4 * N;                        // bytes of a time-domain row
+    constexpr int GSTR = G * ROWT + 16;                // group stride, bytes (odd multiple of 16)
+    constexpr size_t BUF = rtpipe_buf_bytes<PL, X>();
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
+    long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);
+    const int t = threadIdx.x;
+    const int lane8 = t % (8 * G);
+    const int myrow = t - lane8 + G * (lane8 % 8) + lane8 / 8;      // my row of the tile
+    const long tiles = (p.batch + X - 1) / X;
+    const float2 *tw = reinterpret_cast<const float2 *>(p.tw);
+    const float2 *rtw = reinterpret_cast<const float2 *>(p.rtw);
+    float *time_g = C2R ? reinterpret_cast<float *>(p.out0) : const_cast<float *>(reinterpret_cast<const float *>(p.in0));
+    float2 *spec_g = C2R ? const_cast<float2 *>(reinterpret_cast<const float2 *>(p.in0)) : reinterpret_cast<float2 *>(p.out0);
+    auto cta_sync = [&]() { if constexpr (X == 32) __syncwarp(); else __syncthreads(); };
+
+    if (t == 0) {
+        mbar_init(mbar + 0, 1);
+        mbar_init(mbar + 1, 1);
+        fence_proxy_async();
+    }
+    cta_sync();
+
+    auto tile_rows = [&](long tile) { const long row = tile * X; return (p.batch - row < X) ? (int)(p.batch - row) : X; };
+    auto issue = [&](long tile, int st) {              // warp 0, all lanes
+        const int rows = tile_rows(tile);
+        unsigned char *buf = smem_raw + st * BUF;
+        bulk_wait_read_all();                          // stores out of this stage have left shared memory ...
+        __syncwarp();                                  // ... for every lane of the issuing warp
+        if constexpr (!C2R) {
+            if (t == 0) mbar_expect_tx(mbar + st, (uint32_t)(rows * ROWT));
+            __syncwarp();
+            for (int g = t; g * G < rows; g += 32) {
+                const int nr = rows - g * G < G ? rows - g * G : G;
+                tma_load_1d(buf + (size_t)g * GSTR, time_g + (tile * X + (long)g * G) * N, (uint32_t)(nr * ROWT), mbar + st);
+            }
+        } else if (rows == X) {                        // ragged tiles are copied by the threads (see the main loop)
+            if (t == 0) {
+                mbar_expect_tx(mbar + st, (uint32_t)(X * (M + 1) * 8));
+                tma_load_1d(buf, spec_g + tile * X * (M + 1), (uint32_t)(X * (M + 1) * 8), mbar + st);
+            }
+        }
+    };
+
+    claim_and_issue(p.ctr, tiles, slot, 0, issue);
+    unsigned phasebits = 0;
+    cx<R> x[M];
+    for (int it = 0;; it++) {
+        const int st = it & 1;
+        cta_sync();                                    // slot[st] is published; last iteration's stores are issued
+        const long tile = slot[st];
+        if (tile >= tiles) break;
+        unsigned char *buf = smem_raw + st * BUF;
+        const int rows = tile_rows(tile);
+        float2 *dense = reinterpret_cast<float2 *>(buf);
+        float2 *drow = dense + (size_t)myrow * (M + 1);                                   // my spectrum row
+        float4 *trow = reinterpret_cast<float4 *>(buf + (size_t)(myrow / G) * GSTR + (myrow % G) * ROWT);   // my time row
+        if (!C2R || rows == X) {
+            mbar_wait(mbar + st, (phasebits >> st) & 1u);
+            phasebits ^= 1u << st;
+        } else {
+            const float2 *src = spec_g + tile * X * (M + 1);
+            for (int f = t; f < rows * (M + 1); f += X) dense[f] = ld_stream(src + f);
+            cta_sync();
+        }
+
+        if constexpr (!C2R) {
+            static_for<M / 2>([&](auto H_) {
+                CIDX(h, H_);
+                const float4 v = trow[h];
+                x[2 * h] = mk<R>(v.x, v.y);            // z[j] = x[2j] + i x[2j+1]
+                x[2 * h + 1] = mk<R>(v.z, v.w);
+            });
+            claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+            run_pass<R, PL, 0, false>(x, tw, UTw<R, PL>::make(p, tw), 0);
+            cta_sync();                                // time rows and spectrum rows alias
+            const cx<R> z0 = x[slot_of_elem<PL, 0>(0)];
+            drow[0] = make_float2(z0.x + z0.y, 0.0f);
+            drow[M] = make_float2(z0.x - z0.y, 0.0f);
+            const cx<R> xh = RealPost<R>::middle(x[slot_of_elem<PL, 0>(HALF)], ld_tw(rtw + HALF), M);
+            drow[HALF] = make_float2(xh.x, xh.y);
+            static_for<HALF - 1>([&](auto K_) {
+                CIDX(k0, K_);
+                constexpr int k = k0 + 1;
+                const cx<R> z = x[slot_of_elem<PL, 0>(k)], zm = x[slot_of_elem<PL, 0>(M - k)];
+                cx<R> xk, xm;
+                const twd<R> w = ld_tw(rtw + k);
+                RealPost<R>::pair(z, zm, w, w, xk, xm);
+                drow[k] = make_float2(xk.x, xk.y);
+                drow[M - k] = make_float2(xm.x, xm.y);
+            });
+            if (rows == X) {
+                fence_proxy_async();
+                cta_sync();
+                if (t == 0) { tma_store_1d(spec_g + tile * X * (M + 1), buf, (uint32_t)(X * (M + 1) * 8)); bulk_commit(); }
+            } else {
+                cta_sync();
+                float2 *dst = spec_g + tile * X * (M + 1);
+                for (int f = t; f < rows * (M + 1); f += X) st_stream(dst + f, dense[f]);
+            }
+        } else {
+            {   // Hermitian pre-process in registers (scale 0.5/M folded in, :1674)
+                const float sc = 0.5f / float(M);
+                const float2 a0 = drow[0], am = drow[M];      // real parts only (:1679-1684)
+                x[0] = mk<R>((a0.x + am.x) * sc, (a0.x - am.x) * sc);
+                static_for<HALF>([&](auto K_) {
+                    CIDX(k0, K_);
+                    constexpr int k = k0 + 1;                 // 1 .. M/2 (k = M/2 is self-paired)
+                    const float2 a = drow[k], b = drow[M - k];
+                    const twd<R> w = ld_tw(rtw + k);
+                    const float gr = a.x + b.x, gi = a.y - b.y, ur = a.x - b.x, ui = a.y + b.y;
+                    const float hr = fmaf(w.y, ui, w.x * ur), hi = fmaf(w.ny, ur, w.x * ui);
+                    // forward form first, mirrored second: at k = M/2 the mirrored form survives (:1722-1740)
+                    x[k] = mk<R>(sc * (gr - hi), sc * (gi + hr));
+                    x[M - k] = mk<R>(sc * (gr + hi), sc * (hr - gi));
+                });
+            }
+            claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+            run_pass<R, PL, 0, true>(x, tw, UTw<R, PL>::make(p, tw), 0);
+            cta_sync();                                // spectrum rows and time rows alias
+            static_for<M / 2>([&](auto H_) {
+                CIDX(h, H_);
+                constexpr int s0 = slot_of_elem<PL, 0>(2 * h), s1 = slot_of_elem<PL, 0>(2 * h + 1);
+                trow[h] = make_float4(x[s0].x, x[s0].y, x[s1].x, x[s1].y);
+            });
+            fence_proxy_async();
+            cta_sync();
+            if (t < 32) {
+                for (int g = t; g * G < rows; g += 32) {
+                    const int nr = rows - g * G < G ? rows - g * G : G;
+                    tma_store_1d(time_g + (tile * X + (long)g * G) * N, buf + (size_t)g * GSTR, (uint32_t)(nr * ROWT));
+                }
+                bulk_commit();
+            }
+        }
+    }
+    if (t < 32) bulk_wait_read_all();                  // shared memory must outlive the stores that read it
 }
 
 

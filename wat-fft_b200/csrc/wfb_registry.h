@@ -126,6 +126,37 @@ template <class PL, int X, int MINB> struct TileLaunchers {
     }
 };
 
+// persistent, fully TMA-fed thread-per-row c2c (N <= 64)
+template <class PL, int X, int MINB> struct TilePipeLaunchers {
+    static constexpr size_t smem_s = 2 * tpipe_buf_bytes<PL, X, IO_SPLIT>() + 64, smem_i = 2 * tpipe_buf_bytes<PL, X, IO_INTERLEAVED>() + 64;
+    static constexpr size_t smem = smem_s > smem_i ? smem_s : smem_i;
+    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
+        const void *k;
+        if (io == IO_SPLIT)
+            k = dir ? (const void *)k_c2c_tpipe<PL, X, IO_SPLIT, true, MINB> : (const void *)k_c2c_tpipe<PL, X, IO_SPLIT, false, MINB>;
+        else
+            k = dir ? (const void *)k_c2c_tpipe<PL, X, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_tpipe<PL, X, IO_INTERLEAVED, false, MINB>;
+        return launch_persistent(k, smem, X, (batch + X - 1) / X, p, s);
+    }
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), &c2c, nullptr, nullptr};
+    }
+};
+
+// persistent, fully TMA-fed thread-per-row r2c / c2r (N = 64, 128)
+template <class PL, int X, int MINB> struct RealTilePipeLaunchers {
+    static constexpr size_t smem = 2 * rtpipe_buf_bytes<PL, X>() + 64;
+    static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_persistent((const void *)k_real_tpipe<PL, X, false, MINB>, smem, X, (batch + X - 1) / X, p, s);
+    }
+    static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
+        return launch_persistent((const void *)k_real_tpipe<PL, X, true, MINB>, smem, X, (batch + X - 1) / X, p, s);
+    }
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
+    }
+};
+
 // thread-per-row tile kernels for the real transforms (core M <= 64)
 template <class PL, int X, int MINB> struct RealTileLaunchers {
     static constexpr size_t smem = sizeof(float) * (size_t)(2 * PL::N + 4) * X;
