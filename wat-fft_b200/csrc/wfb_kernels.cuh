@@ -847,9 +847,14 @@ template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr s
     return (a + 127) / 128 * 128;
 }
 
-template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, bool RC = false>
+// TS ("TMA stores"): the results go back into the tile's stage buffer (same layout as the input) and leave as bulk
+// stores issued after the next loop-top barrier, instead of per-thread STG; the stage is refilled once those
+// stores have drained (cp.async.bulk.wait_group.read), which the issuing lanes check after the row loads of the
+// following tile.
+template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, bool RC = false, bool TS = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
+    static_assert(!TS || RT<R>::LANES == 1, "TMA stores: scalar lanes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using S = typename VecOf<R>::s;
     using V2 = typename VecOf<R>::v2;
@@ -884,6 +889,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         constexpr int PLANES = (IO == IO_SPLIT) ? 2 : 1;
         constexpr uint32_t ROWB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * N * sizeof(S));     // bytes per row per plane
         constexpr uint32_t RSB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * RSTR * sizeof(S));  // smem row stride, bytes
+        if constexpr (TS) { bulk_wait_read_all(); __syncwarp(); }   // the stores out of this stage have drained
         if constexpr (!RC) {
             if (threadIdx.x == 0) {
                 mbar_expect_tx(mbar + st, PLANES * rows * ROWB);
@@ -904,6 +910,32 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         }
     };
 
+    // TS: bulk-store the finished tile sitting in stage st (warp 0; same copy granularity as the loads)
+    auto store_tile = [&](long tile, int st) {
+        const long row = tile * ROWS;
+        const int rows = (p.batch - row < ROWS) ? (int)(p.batch - row) : ROWS;
+        const unsigned char *src = smem_raw + st * BUF;
+        constexpr int PLANES = (IO == IO_SPLIT) ? 2 : 1;
+        constexpr uint32_t ROWB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * N * sizeof(S));
+        constexpr uint32_t RSB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * RSTR * sizeof(S));
+        if (threadIdx.x < 32) {
+            if constexpr (!RC) {
+                if (threadIdx.x == 0) {
+                    tma_store_1d(reinterpret_cast<unsigned char *>(p.out0) + row * ROWB, src, rows * ROWB);
+                    if constexpr (PLANES == 2)
+                        tma_store_1d(reinterpret_cast<unsigned char *>(p.out1) + row * ROWB, src + ROWS * RSB, rows * ROWB);
+                }
+            } else {
+                for (int c = threadIdx.x; c < PLANES * rows; c += 32) {
+                    const int pl = c / rows, r = c - pl * rows;
+                    unsigned char *dst = reinterpret_cast<unsigned char *>(pl ? p.out1 : p.out0) + (row + r) * ROWB;
+                    tma_store_1d(dst, src + (size_t)(pl * ROWS + r) * RSB, ROWB);
+                }
+            }
+            bulk_commit();
+        }
+    };
+
     static_assert(PL::T * X >= 32, "tile claims are made by a full warp");
     long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
     claim_and_issue(p.ctr, tiles, slot, 0, issue);
@@ -914,9 +946,10 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         const int st = it & 1;
         fence_proxy_async();      // our generic-proxy accesses to the other stage precede its refill
         __syncthreads();          // ... and everyone is done using it as scratch
+        if constexpr (TS) { if (it > 0) store_tile(slot[st ^ 1], st ^ 1); }   // last iteration's results (all written: barrier above)
         const long tile = slot[st];
         if (tile >= tiles) break;
-        claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+        if constexpr (!TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
         mbar_wait(mbar + st, (it >> 1) & 1);
 
         const long row = tile * ROWS + (long)xi * LANES;
@@ -951,11 +984,38 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         }
         // the dense input tile and the padded per-group scratch regions alias: every group must
         // have its inputs in registers before any group spills
-        if constexpr (PL::npass() > 1) __syncthreads();
+        if constexpr (PL::npass() > 1 || TS) __syncthreads();
+        // TS: slot[st ^ 1] still names the tile just stored; the claim overwrites it only now, after the barrier
+        if constexpr (TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(N);
         run_all<R, PL, PADQ, X, INV>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
 
-        if (active) {
+        if constexpr (TS) {
+            // results -> the tile's rows in the stage buffer (they alias every group's scratch)
+            if constexpr (PL::npass() > 1) __syncthreads();
+            const R sc = RT<R>::splat((S)p.scale);
+            if constexpr (IO == IO_SPLIT) {
+                S *re = reinterpret_cast<S *>(buf) + (size_t)xi * RSTR + tid;
+                S *im = re + ROWS * RSTR;
+                static_for<PL::E>([&](auto S_) {
+                    CIDX(slot_, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot_);
+                    cx<R> v = x[slot_];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    re[e * PL::T] = v.x; im[e * PL::T] = v.y;
+                });
+            } else {
+                V2 *z = reinterpret_cast<V2 *>(buf) + (size_t)xi * RSTR + tid;
+                static_for<PL::E>([&](auto S_) {
+                    CIDX(slot_, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot_);
+                    cx<R> v = x[slot_];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    V2 o; o.x = v.x; o.y = v.y;
+                    z[e * PL::T] = o;
+                });
+            }
+        } else if (active) {
             const long rs = two ? N : 0;
             const R sc = RT<R>::splat((S)p.scale);
             if constexpr (IO == IO_SPLIT) {
@@ -980,6 +1040,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
             }
         }
     }
+    if constexpr (TS) { if (threadIdx.x < 32) bulk_wait_read_all(); }   // shared memory must outlive the stores that read it
 }
 
 
@@ -1143,7 +1204,11 @@ template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ c
     return (a + 127) / 128 * 128;
 }
 
-template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false>
+// TS ("TMA stores", as in k_c2c_pipe): results are assembled as a dense tile in the stage buffer and leave as ONE
+// bulk store after the next loop-top barrier.  r2c: each row's (M+1) bins; the mirrored halves are parked in the
+// row's own slots [1, M/2], and the thread that reads park[k] is the one that overwrites it with X[k], so the
+// post-process is in place.  c2r: the M complex (= N real) outputs of each row.
+template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false, bool TS = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
     static_assert(!C2R || X % 2 == 0, "c2r tiles need an even number of rows (16-byte alignment)");
@@ -1162,6 +1227,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     const typename RT<R>::twel *rtw = reinterpret_cast<const typename RT<R>::twel *>(p.rtw);
     const long tiles = (p.batch + X - 1) / X;
     const V2 *gin = reinterpret_cast<const V2 *>(p.in0);
+    constexpr int OUT_ROW = C2R ? M : M + 1;         // row lengths of the result tile, complex values
+    V2 *gout = reinterpret_cast<V2 *>(p.out0);
 
     if (threadIdx.x == 0) {
         mbar_init(mbar + 0, 1);
@@ -1173,6 +1240,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     auto tile_rows = [&](long tile) { const long row = tile * X; return (p.batch - row < X) ? (int)(p.batch - row) : X; };
     auto tma_ok = [&](long tile) { return !C2R || (tile_rows(tile) % 2 == 0); };
     auto issue = [&](long tile, int st) {
+        if constexpr (TS) { bulk_wait_read_all(); __syncwarp(); }   // the stores out of this stage have drained
         if (!tma_ok(tile)) return;
         const int rows = tile_rows(tile);
         if constexpr (!RC) {
@@ -1192,6 +1260,19 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
         }
     };
 
+    // TS: the finished tile in stage st leaves as one bulk store (odd-sized last r2c tile: plain stores by warp 0)
+    auto store_tile = [&](long tile, int st) {
+        if (threadIdx.x >= 32) return;
+        const int count = tile_rows(tile) * OUT_ROW;
+        const V2 *src = reinterpret_cast<const V2 *>(smem_raw + st * BUF);
+        V2 *dst = gout + tile * X * OUT_ROW;
+        if ((count * sizeof(V2)) % 16 == 0) {
+            if (threadIdx.x == 0) { tma_store_1d(dst, src, (uint32_t)(count * sizeof(V2))); bulk_commit(); }
+        } else {
+            for (int i = threadIdx.x; i < count; i += 32) st_stream(dst + i, src[i]);
+        }
+    };
+
     static_assert(PL::T * X >= 32, "tile claims are made by a full warp");
     long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
     claim_and_issue(p.ctr, tiles, slot, 0, issue);
@@ -1201,9 +1282,10 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
         const int st = it & 1;
         fence_proxy_async();
         __syncthreads();
+        if constexpr (TS) { if (it > 0) store_tile(slot[st ^ 1], st ^ 1); }   // last iteration's results (all written: barrier above)
         const long tile = slot[st];
         if (tile >= tiles) break;
-        claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+        if constexpr (!TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
         unsigned char *buf = smem_raw + st * BUF;
         if (tma_ok(tile)) {
             mbar_wait(mbar + st, (phasebits >> st) & 1u);
@@ -1223,8 +1305,11 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             // ---------------- r2c
             static_for<PL::E>([&](auto E_) { CIDX(e, E_); const V2 a = raw[tid + e * PL::T]; x[e] = mk<R>(a.x, a.y); });
             __syncthreads();                           // dense tile and padded scratch alias
+            if constexpr (TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);   // (slot[st ^ 1] was read before the barrier)
             run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
-            if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
+            // TS: the result rows are dense ([X][M+1]) and alias the other groups' scratch
+            cx<R> *park = TS ? reinterpret_cast<cx<R> *>(buf) + (size_t)xi * (M + 1) : scratch;
+            if (PL::npass() > 1) { if constexpr (TS && X > 1) __syncthreads(); else sync_transform<PL::T, X>(xi); }
             // Hermitian post-process: bin k = tid + i*T (k < M/2) pairs the thread's OWN register value Z[k] with
             // Z[M-k], which another thread of the group owns.  Only the upper half (elements >= M/2) travels
             // through shared memory: half a spill and half a re-read instead of a full spill and two full reads.
@@ -1234,30 +1319,31 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             static_for<PL::E>([&](auto S_) {
                 CIDX(slot, S_);
                 constexpr int e = out_elem<PL, LAST>(slot);
-                if constexpr (e >= PL::E / 2) scratch[M - e * PL::T - tid] = x[slot];
+                if constexpr (e >= PL::E / 2) park[M - e * PL::T - tid] = x[slot];
             });
             sync_transform<PL::T, X>(xi);
-            if (active) {
-                V2 *out = reinterpret_cast<V2 *>(p.out0) + row * (M + 1);
+            if (active || TS) {
+                V2 *out = TS ? reinterpret_cast<V2 *>(park) : reinterpret_cast<V2 *>(p.out0) + row * (M + 1);
                 constexpr int HALF = M / 2;
                 constexpr int PER = PL::E / 2;
                 static_assert(PER * PL::T == HALF, "bins per thread");
                 const R zero = RT<R>::splat(0);
+                auto put = [&](V2 *q, cx<R> v) { if constexpr (TS) { V2 o; o.x = v.x; o.y = v.y; *q = o; } else GIO<R>::st_il(q, 0, false, v); };
                 static_for<PER>([&](auto I_) {
                     CIDX(i, I_);
                     const int k = tid + i * PL::T;
                     const cx<R> z = x[slot_of_elem<PL, LAST>(i)];
                     if (i == 0 && k == 0) {
-                        GIO<R>::st_il(out, 0, false, mk<R>(radd(z.x, z.y), zero));
-                        GIO<R>::st_il(out + M, 0, false, mk<R>(rsub(z.x, z.y), zero));
-                        const cx<R> zh = scratch[HALF];
-                        GIO<R>::st_il(out + HALF, 0, false, RealPost<R>::middle(zh, ld_tw(rtw + HALF), M));
+                        put(out, mk<R>(radd(z.x, z.y), zero));
+                        put(out + M, mk<R>(rsub(z.x, z.y), zero));
+                        const cx<R> zh = park[HALF];
+                        put(out + HALF, RealPost<R>::middle(zh, ld_tw(rtw + HALF), M));
                     } else {
-                        const cx<R> zm = scratch[k];
+                        const cx<R> zm = park[k];
                         cx<R> xk, xm;
                         RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);
-                        GIO<R>::st_il(out + k, 0, false, xk);
-                        GIO<R>::st_il(out + (M - k), 0, false, xm);
+                        put(out + k, xk);
+                        put(out + (M - k), xm);
                     }
                 });
             }
@@ -1286,6 +1372,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
                 }
             });
             __syncthreads();                           // every group has consumed its raw rows
+            if constexpr (TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
             static_for<PER>([&](auto I_) {
                 CIDX(i, I_);
                 const int k = tid + i * PL::T;
@@ -1295,7 +1382,16 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             sync_transform<PL::T, X>(xi);
             static_for<PER>([&](auto E_) { CIDX(e, E_); x[PER + e] = scratch[M - (PER + e) * PL::T - tid]; });
             run_all<R, PL, PADQ, X, true>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, true);
-            if (active) {
+            if constexpr (TS) {
+                if constexpr (X > 1) __syncthreads(); else sync_transform<PL::T, X>(xi);   // result rows alias the scratch
+                V2 *z = reinterpret_cast<V2 *>(buf) + (size_t)xi * M + tid;
+                static_for<PL::E>([&](auto S_) {
+                    CIDX(slot_, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot_);
+                    V2 o; o.x = x[slot_].x; o.y = x[slot_].y;
+                    z[e * PL::T] = o;
+                });
+            } else if (active) {
                 V2 *z = reinterpret_cast<V2 *>(p.out0) + row * M + tid;
                 static_for<PL::E>([&](auto S_) {
                     CIDX(slot, S_);
@@ -1305,6 +1401,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             }
         }
     }
+    if constexpr (TS) { if (threadIdx.x < 32) bulk_wait_read_all(); }   // shared memory must outlive the stores that read it
 }
 
 

@@ -5,6 +5,7 @@ namespace wfb {
 #define VPR(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, true>::make(#PL "_pipe" #X "_rc", PRIO)
 #define VP64(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, false, 64>::make(#PL "_pipe" #X, PRIO)
 #define VP32(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, false, 32>::make(#PL "_pipe" #X, PRIO)
+#define VTS(PL, X, MINB, RC, PQ, PRIO) PipeLaunchers<float, PL, X, MINB, RC, PQ, true>::make(#PL "_pipe" #X "_ts", PRIO)
 #define VP2(PL, X, MINB, PRIO) PipeLaunchers<f32x2, PL, X, MINB>::make(#PL "_pipe" #X "_x2", PRIO)
 const std::vector<Variant> &variants_f32_pipe() {
     // 16 KB tiles are the sweet spot for the dynamically scheduled pipeline (8 KB and 32 KB tiles lose 10-30 %).
@@ -19,6 +20,10 @@ const std::vector<Variant> &variants_f32_pipe() {
         VP(F32_1024, 2, 2, 33),
         VP(F32_2048, 1, 4, 30),
         VP(F32_4096, 1, 2, 30), VP(F32_8192, 1, 1, 30),
+        // results leave through the stage buffer as bulk stores instead of per-thread STG
+        // (profiles/: +1..4 % at burst clocks, +3..8 % power-capped; N = 4096: 86 -> 92 % at burst, equal power-capped)
+        VTS(F32_128, 16, 2, true, 16, 60), VTS(F32_256, 8, 2, false, 16, 60), VTS(P32_512, 4, 2, false, 16, 60), VTS(P32_1024, 2, 2, false, 32, 60),
+        VTS(F32_2048, 1, 4, false, 16, 60), VTS(P64_4096, 1, 1, false, 64, 20), VTS(F32_4096, 1, 2, false, 16, 60),
         VP64(P64_4096, 1, 1, 31),   // one exchange: 3 % slower than F32_4096_pipe1 at burst clocks, 4 % faster power-capped
          VP64(P64_2048, 1, 1, 20), VP64(P64_1024, 2, 1, 20),
     };

@@ -3,11 +3,16 @@
 namespace wfb {
 #define VP(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB>::make(#PL "_pipe" #X, PRIO)
 #define VR(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB>::make(#PL "_rpipe" #X, __VA_ARGS__)
+#define VTS(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_pipe" #X "_ts", PRIO)
+#define VRTS(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_rpipe" #X "_ts", __VA_ARGS__)
 const std::vector<Variant> &variants_f64_pipe() {
     // priorities from the sweeps in profiles/ (c2c N = 256: the direct kernel wins; real transforms: the pipelined
     // kernels win up to N = 2048 since the Hermitian step moves only half its data through shared memory)
     static const std::vector<Variant> v = {
         VP(F64_256, 8, 2, 5), VP(F64_512, 4, 2, 30), VP(F64_1024, 2, 2, 30), VP(F64_2048, 1, 2, 30), VP(F64_4096, 1, 1, 30),
+        // results leave as bulk stores out of the stage buffer (see k_c2c_pipe / k_real_pipe, TS): defaults from N = 256
+        VTS(F64_256, 8, 2, 60), VTS(F64_512, 4, 2, 60), VTS(F64_1024, 2, 2, 60), VTS(F64_2048, 1, 2, 60), VTS(F64_4096, 1, 1, 60),
+        VRTS(F64_128, 16, 2, 60), VRTS(F64_256, 8, 2, 60), VRTS(F64_512, 4, 2, 60), VRTS(F64_1024, 2, 2, 60), VRTS(F64_2048, 2, 1, 60),
         VR(F64_128, 16, 2, 30), VR(F64_256, 8, 2, 30), VR(F64_512, 4, 2, 5, 30), VR(F64_1024, 2, 2, 30), VR(F64_2048, 2, 1, 5),
     };
     return v;
