@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Parity of EVERY compiled kernel variant (not just the default) against the CPU oracle."""
 import math
+import os
 import sys
 from pathlib import Path
 
@@ -14,6 +15,7 @@ C = wf._cabi
 O = Oracle()
 rng = np.random.default_rng(0)
 bad = 0
+VERBOSE = bool(os.environ.get("WFB_CHECK_VERBOSE"))   # print every worst error as a fraction of its bound
 
 
 def rel(a, b, x):
@@ -47,7 +49,7 @@ for n in sizes:
                         worst = max(worst, rel(plan.host(0).reshape(b, 2 * n)[r], O.fft_interleaved_f32(il[r], inv), il[r]))
                 ok = worst <= 2e-6 * math.log2(n)
                 bad += (not ok)
-                row.append(f"{vn}{'/il' if layout else ''}{'/inv' if inv else ''}:{'ok' if ok else 'FAIL %.2e' % worst}")
+                row.append(f"{vn}{'/il' if layout else ''}{'/inv' if inv else ''}:{('ok %.3f' % (worst / (2e-6 * math.log2(n))) if VERBOSE else 'ok') if ok else 'FAIL %.2e' % worst}")
         plan.destroy()
     print(n, " ".join(row), flush=True)
 # real transforms and f64: every variant against the oracle
@@ -67,7 +69,7 @@ for n in sizes:
             t = plan.host(C.BUF_TIME).reshape(b, n)
             w2 = max(rel(t[r], O.irfft_split_f32(spec[r]), spec[r]) for r in range(b))
             ok = max(w1, w2) <= 2e-6 * math.log2(n); bad += (not ok)
-            row.append(f"r2c:{vn}:{'ok' if ok else 'FAIL %.2e %.2e' % (w1, w2)}")
+            row.append(f"r2c:{vn}:{('ok %.3f %.3f' % (w1 / (2e-6 * math.log2(n)), w2 / (2e-6 * math.log2(n))) if VERBOSE else 'ok') if ok else 'FAIL %.2e %.2e' % (w1, w2)}")
         plan.destroy()
     d = rng.uniform(-1, 1, (b, 2 * n))
     if n <= 8192:

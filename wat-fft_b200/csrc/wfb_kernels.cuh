@@ -235,6 +235,20 @@ WFB_FUSED_R4(float)
 WFB_FUSED_R4(double)
 #undef WFB_FUSED_R4
 
+// Large f32 cores (N >= 2048) are bound by the L1/shared-memory data pipe (ncu: 81-91 % busy, a quarter of it
+// twiddle loads), so for the per-thread twiddles of a radix-4 stage only w1 is loaded and w2 = w1^2, w3 = w1*w2
+// are formed in registers (8 FP instructions for two 8-byte loads).  The reference LOOKS UP all three
+// (fft_split_native_f32.wat:225-252), each carrying the Taylor error of its own angle (5e-7); the derived ones
+// carry 2-3x the error of w1 instead.  Measured against the oracle: 12-21 % of the parity bound instead of
+// 2-8 %; c2c N = 4096 goes from 92 % to 102 % of the measured HBM peak.  f64 keeps the tables (its parity
+// bound is 1e4 times tighter than the twiddle error), and so do all smaller f32 sizes.
+#ifndef WFB_DERIVE_MIN_N
+#define WFB_DERIVE_MIN_N 2048
+#endif
+template <typename R, class PL> __host__ __device__ constexpr bool derive_tw() {
+    return sizeof(typename RT<R>::scalar) == 4 && RT<R>::LANES == 1 && PL::N >= WFB_DERIVE_MIN_N;
+}
+
 // ----------------------------------------------------------------------------------------
 // one fused pass over the E register-resident values of a thread
 // ----------------------------------------------------------------------------------------
@@ -271,8 +285,13 @@ __device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>
                 } else if constexpr (!unit) {
                     w1 = ld_tw(twj + (off + L_IN * c));
                     if constexpr (r == 4) {
-                        w2 = ld_tw(twj + (off + lq + L_IN * c));
-                        w3 = ld_tw(twj + (off + 2 * lq + L_IN * c));
+                        if constexpr (derive_tw<R, PL>()) {
+                            w2.x = rfma(w1.x, w1.x, rneg(rmul(w1.y, w1.y))); w2.y = rmul(radd(w1.x, w1.x), w1.y); w2.ny = rneg(w2.y);
+                            w3.x = rfma(w1.x, w2.x, rneg(rmul(w1.y, w2.y))); w3.y = rfma(w1.x, w2.y, rmul(w1.y, w2.x)); w3.ny = rneg(w3.y);
+                        } else {
+                            w2 = ld_tw(twj + (off + lq + L_IN * c));
+                            w3 = ld_tw(twj + (off + 2 * lq + L_IN * c));
+                        }
                     }
                 }
                 static_for<w>([&](auto LO_) {
@@ -393,7 +412,8 @@ struct KParams {
 // pass-0 twiddle source of a kernel with lane type R and plan PL
 template <typename R, class PL> struct UTw {
     static constexpr int ENTRIES = PL::tw_off(1, 0);   // table entries of pass 0
-    static constexpr int LIMIT = RT<R>::LANES != 1 ? 0 : (ENTRIES <= 31 ? ENTRIES : WFB_CTW_LIMIT64);
+    // thread-per-row plans (T == 1) have no other warp to hide a load behind: constants pay there even at 63 entries
+    static constexpr int LIMIT = RT<R>::LANES != 1 ? 0 : ((ENTRIES <= 31 || PL::T == 1) ? ENTRIES : WFB_CTW_LIMIT64);
     static_assert(LIMIT * sizeof(typename RT<R>::twel) <= KParams::TW0_BYTES, "tw0 capacity");
     static __device__ __forceinline__ HTw<R, LIMIT> make(const KParams &p, const typename RT<R>::twel *tw) {
         return {reinterpret_cast<const typename RT<R>::twel *>(p.tw0), tw};
@@ -832,11 +852,24 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // schedule lets CTAs drift apart; tools/microbench/copy_pipe.cu measures 6.05 TB/s (static) vs 6.85 TB/s
 // (dynamic) for the same TMA-pipelined copy.  Called by warp 0; the claim for the NEXT tile is made when
 // its prefetch is issued, one iteration ahead, and published to the CTA through `slot[stage]`.
-template <class IssueFn>
-__device__ __forceinline__ void claim_and_issue(unsigned long long *ctr, long tiles, long *slot, int st, IssueFn &&issue) {
+// EARLY: the claim itself is software-pipelined -- the atomic whose result is consumed here was fired one claim
+// earlier (`pending`, thread 0), so the issuing warp never waits for the round trip to L2.  In the one-warp CTAs
+// of the thread-per-row kernels that wait stalls the whole CTA once per tile (power-capped: +3..5 % at N = 32..128).
+// For the large transforms it is a loss (r2c N = 4096: -4.6 %): a claim made a whole tile early widens the window
+// of rows the GPU works on at any moment, the very thing the dynamic schedule is there to keep tight.
+template <bool EARLY> __device__ __forceinline__ long claim_prime(unsigned long long *ctr) {
+    return (EARLY && threadIdx.x == 0) ? (long)atomicAdd(ctr, 1ULL) : 0L;
+}
+template <bool EARLY, class IssueFn>
+__device__ __forceinline__ void claim_and_issue(unsigned long long *ctr, long &pending, long tiles, long *slot, int st, IssueFn &&issue) {
     if (threadIdx.x < 32) {
         long tn = 0;
-        if (threadIdx.x == 0) { tn = (long)atomicAdd(ctr, 1ULL); slot[st] = tn; }
+        if constexpr (EARLY) {
+            tn = pending;
+            if (threadIdx.x == 0) { pending = (long)atomicAdd(ctr, 1ULL); slot[st] = tn; }
+        } else {
+            if (threadIdx.x == 0) { tn = (long)atomicAdd(ctr, 1ULL); slot[st] = tn; }
+        }
         tn = __shfl_sync(0xffffffffu, tn, 0);
         if (tn < tiles) issue(tn, st);
     }
@@ -938,7 +971,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
 
     static_assert(PL::T * X >= 32, "tile claims are made by a full warp");
     long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
-    claim_and_issue(p.ctr, tiles, slot, 0, issue);
+    long pending = claim_prime<(PL::N <= 256)>(p.ctr);
+    claim_and_issue<(PL::N <= 256)>(p.ctr, pending, tiles, slot, 0, issue);
     cx<R> x[PL::E];
     // (hoisting the last pass's thread-invariant twiddles into registers was tried and measured
     //  neutral at N = 4096 and 3-6 % slower below, from the extra 27 registers: profiles/r01_sweep.md)
@@ -949,7 +983,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         if constexpr (TS) { if (it > 0) store_tile(slot[st ^ 1], st ^ 1); }   // last iteration's results (all written: barrier above)
         const long tile = slot[st];
         if (tile >= tiles) break;
-        if constexpr (!TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+        if constexpr (!TS) claim_and_issue<(PL::N <= 256)>(p.ctr, pending, tiles, slot, st ^ 1, issue);
         mbar_wait(mbar + st, (it >> 1) & 1);
 
         const long row = tile * ROWS + (long)xi * LANES;
@@ -986,7 +1020,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         // have its inputs in registers before any group spills
         if constexpr (PL::npass() > 1 || TS) __syncthreads();
         // TS: slot[st ^ 1] still names the tile just stored; the claim overwrites it only now, after the barrier
-        if constexpr (TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+        if constexpr (TS) claim_and_issue<(PL::N <= 256)>(p.ctr, pending, tiles, slot, st ^ 1, issue);
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(N);
         run_all<R, PL, PADQ, X, INV>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
 
@@ -1115,7 +1149,8 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
         }
     };
 
-    claim_and_issue(p.ctr, tiles, slot, 0, issue);
+    long pending = claim_prime<true>(p.ctr);
+    claim_and_issue<true>(p.ctr, pending, tiles, slot, 0, issue);
     unsigned phasebits = 0;
     cx<R> x[N];
     for (int it = 0;; it++) {
@@ -1145,7 +1180,7 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
                 x[2 * h] = mk<R>(v.x, v.y); x[2 * h + 1] = mk<R>(v.z, v.w);
             });
         }
-        claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);       // refill the other stage while this tile computes
+        claim_and_issue<true>(p.ctr, pending, tiles, slot, st ^ 1, issue);       // refill the other stage while this tile computes
 
         run_pass<R, PL, 0, INV>(x, tw, UTw<R, PL>::make(p, tw), 0);
 
@@ -1275,7 +1310,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
 
     static_assert(PL::T * X >= 32, "tile claims are made by a full warp");
     long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
-    claim_and_issue(p.ctr, tiles, slot, 0, issue);
+    long pending = claim_prime<false>(p.ctr);
+    claim_and_issue<false>(p.ctr, pending, tiles, slot, 0, issue);
     cx<R> x[PL::E];
     unsigned phasebits = 0;                            // mbarrier phase parity per stage (bit st)
     for (int it = 0;; it++) {
@@ -1285,7 +1321,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
         if constexpr (TS) { if (it > 0) store_tile(slot[st ^ 1], st ^ 1); }   // last iteration's results (all written: barrier above)
         const long tile = slot[st];
         if (tile >= tiles) break;
-        if constexpr (!TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+        if constexpr (!TS) claim_and_issue<false>(p.ctr, pending, tiles, slot, st ^ 1, issue);
         unsigned char *buf = smem_raw + st * BUF;
         if (tma_ok(tile)) {
             mbar_wait(mbar + st, (phasebits >> st) & 1u);
@@ -1305,7 +1341,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             // ---------------- r2c
             static_for<PL::E>([&](auto E_) { CIDX(e, E_); const V2 a = raw[tid + e * PL::T]; x[e] = mk<R>(a.x, a.y); });
             __syncthreads();                           // dense tile and padded scratch alias
-            if constexpr (TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);   // (slot[st ^ 1] was read before the barrier)
+            if constexpr (TS) claim_and_issue<false>(p.ctr, pending, tiles, slot, st ^ 1, issue);   // (slot[st ^ 1] was read before the barrier)
             run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
             // TS: the result rows are dense ([X][M+1]) and alias the other groups' scratch
             cx<R> *park = TS ? reinterpret_cast<cx<R> *>(buf) + (size_t)xi * (M + 1) : scratch;
@@ -1372,7 +1408,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
                 }
             });
             __syncthreads();                           // every group has consumed its raw rows
-            if constexpr (TS) claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+            if constexpr (TS) claim_and_issue<false>(p.ctr, pending, tiles, slot, st ^ 1, issue);
             static_for<PER>([&](auto I_) {
                 CIDX(i, I_);
                 const int k = tid + i * PL::T;
@@ -1624,7 +1660,8 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
         }
     };
 
-    claim_and_issue(p.ctr, tiles, slot, 0, issue);
+    long pending = claim_prime<true>(p.ctr);
+    claim_and_issue<true>(p.ctr, pending, tiles, slot, 0, issue);
     unsigned phasebits = 0;
     cx<R> x[M];
     for (int it = 0;; it++) {
@@ -1653,7 +1690,7 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
                 x[2 * h] = mk<R>(v.x, v.y);            // z[j] = x[2j] + i x[2j+1]
                 x[2 * h + 1] = mk<R>(v.z, v.w);
             });
-            claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+            claim_and_issue<true>(p.ctr, pending, tiles, slot, st ^ 1, issue);
             run_pass<R, PL, 0, false>(x, tw, UTw<R, PL>::make(p, tw), 0);
             cta_sync();                                // time rows and spectrum rows alias
             const cx<R> z0 = x[slot_of_elem<PL, 0>(0)];
@@ -1697,7 +1734,7 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
                     x[M - k] = mk<R>(sc * (gr + hi), sc * (hr - gi));
                 });
             }
-            claim_and_issue(p.ctr, tiles, slot, st ^ 1, issue);
+            claim_and_issue<true>(p.ctr, pending, tiles, slot, st ^ 1, issue);
             run_pass<R, PL, 0, true>(x, tw, UTw<R, PL>::make(p, tw), 0);
             cta_sync();                                // spectrum rows and time rows alias
             static_for<M / 2>([&](auto H_) {
@@ -1861,7 +1898,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
     };
 
     long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);   // tile claimed for each stage
-    claim_and_issue(sp.ctr, tiles, slot, 0, issue);
+    long pending = claim_prime<false>(sp.ctr);
+    claim_and_issue<false>(sp.ctr, pending, tiles, slot, 0, issue);
     cx<R> x[PL::E];
     const float2 *win = reinterpret_cast<const float2 *>(sp.window);
     for (int it = 0;; it++) {
@@ -1870,7 +1908,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
         __syncthreads();
         const long tile = slot[st];
         if (tile >= tiles) break;
-        claim_and_issue(sp.ctr, tiles, slot, st ^ 1, issue);
+        claim_and_issue<false>(sp.ctr, pending, tiles, slot, st ^ 1, issue);
         mbar_wait(mbar + st, (it >> 1) & 1);
         unsigned char *buf = smem_raw + st * BUF;
         const long frame = tile * X + xi;
