@@ -286,7 +286,7 @@ def run_ours(args):
     for i, n in enumerate(SIZES):
         for d, nm in ((0, "fwd"), (1, "inv")):
             ms = statistics.fmean(evs[k][2 * i + d].elapsed_time(evs[k][2 * i + d + 1]) for k in range(K))
-            per_kernel.append({"kernel": f"k_c2c<f32,N={n},split,{nm}>", "n": n, "dir": nm, "ms": ms,
+            per_kernel.append({"kernel": f"k_c2c<f32,N={n},split,{nm}>", "variant": plans[n].current_variant(d), "n": n, "dir": nm, "ms": ms,
                                "GBs": bytes_per_launch / ms / 1e6, "Mtransforms_s": (GIB // (8 * n)) / ms / 1e3})
     peak, peak_src = peaks()
     dom = max(per_kernel, key=lambda r: r["ms"])
@@ -296,7 +296,7 @@ def run_ours(args):
         traffic = prof.get(dom["kernel"])
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBs"], "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "variant": dom["variant"], "achieved": dom["GBs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "share_of_step": dom["ms"] / ms_per_step,

@@ -124,6 +124,8 @@ WFB_API void *wfb_plan_stream(wfb_plan *plan);
 WFB_API int wfb_plan_variant_count(wfb_plan *plan);
 WFB_API int wfb_plan_set_variant(wfb_plan *plan, int variant);
 WFB_API const char *wfb_plan_variant_name(wfb_plan *plan, int variant);
+/* Index of the variant wfb_exec(plan, direction, ...) launches (the two directions may default to different kernels). */
+WFB_API int wfb_plan_current_variant(wfb_plan *plan, int direction);
 /* Algorithmic bytes one exec moves (one read + one write of the payload; twiddles excluded). */
 WFB_API size_t wfb_plan_algorithmic_bytes(wfb_plan *plan);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */

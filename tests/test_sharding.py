@@ -53,7 +53,8 @@ def test_world_size_2_gloo(tmp_path):
         dist.all_reduce(rows)
         assert int(rows.item()) == batch
         dist.destroy_process_group()
-        print("rank", rank, "ok")
+        sys.stdout.write("rank %d ok\\n" % rank)      # one write: the two ranks share the pipe
+        sys.stdout.flush()
     """))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     import socket

@@ -49,6 +49,7 @@ SYMBOLS = {
     "wfb_plan_variant_count": (ctypes.c_int, [ctypes.c_void_p]),
     "wfb_plan_set_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "wfb_plan_variant_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
+    "wfb_plan_current_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "wfb_plan_algorithmic_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
     "wfb_kernel_launch_count": (ctypes.c_ulonglong, []),
     "wfb_reference_twiddles": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2),

@@ -70,6 +70,10 @@ class Plan:
     def variants(self):
         return [self._lib.wfb_plan_variant_name(self._p, i).decode() for i in range(self._lib.wfb_plan_variant_count(self._p))]
 
+    def current_variant(self, direction=0):
+        """name of the kernel variant exec(direction) launches"""
+        return self.variants()[self._lib.wfb_plan_current_variant(self._p, direction)]
+
     def set_variant(self, i):
         C.check(self._lib.wfb_plan_set_variant(self._p, i))
 

@@ -432,6 +432,10 @@ int wfb_plan_set_variant(wfb_plan *pl, int v) {
     pl->variant_inv = v;
     return WFB_OK;
 }
+int wfb_plan_current_variant(wfb_plan *pl, int direction) {
+    if (!pl || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
+    return direction == WFB_INVERSE ? pl->variant_inv : pl->variant;
+}
 const char *wfb_plan_variant_name(wfb_plan *pl, int v) {
     if (!pl || v < 0 || v >= (int)pl->variants.size()) return "";
     return pl->variants[v]->name;
@@ -527,6 +531,8 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
     static const long chunk_bytes = [] { const char *e = getenv("WFB_STAGE_CHUNK_MB"); long v = e ? atol(e) : 32; return (v < 1 ? 1 : v) << 20; }();
     static const int nstreams = [] { const char *e = getenv("WFB_STAGE_STREAMS"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > wfb_plan::NPIPE ? (int)wfb_plan::NPIPE : v); }();
     long chunk = (long)(chunk_bytes / (long)widest);
+    // whole tiles per chunk (tiles hold up to 256 rows) and 16-byte aligned chunk starts for the (n+2)-wide spectrum rows
+    if (chunk >= 512) chunk &= ~255L; else if (chunk >= 2) chunk &= ~1L;
     if (chunk < 1) chunk = 1;
     const bool pipelined = (h2d || d2h) && pl->batch > 2 * chunk;
     if (!pipelined) {
