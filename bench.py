@@ -170,7 +170,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -359,10 +359,29 @@ def run_ours(args):
     if n_gpus == 1 and not args.no_cpu_baseline:
         v, cores, kind, sample, _ = cpu_reference_run(steps=3, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version banner there on
+    the first collective, whatever NCCL_DEBUG_FILE says) are sent to stderr for the rest of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
@@ -374,6 +393,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl == "ours" and args.gpus > 1 and world == 1):      # (the torchrun re-launch prints through its ranks)
+        quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and world == 1:
