@@ -899,6 +899,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
     // 32/T rows a warp reads side by side start T banks apart (a dense tile puts every row on
     // bank 0: ncu showed 4-way conflicts and mio_throttle as the top stall at N = 128)
     constexpr int RSTR = RC ? N + N / 16 : N;       // smem row stride, elements
+    static_assert(!RC || RSTR <= padded_size<PADQ>(N), "padded rows must fit the stage buffer (sized for the scratch)");
     static_assert(!RC || (N >= 64 && PL::T * X >= 32), "row copies need 16-byte aligned padded rows and a full issuing warp");
     constexpr size_t BUF = pipe_buf_bytes<R, PL, PADQ, X>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
@@ -1255,6 +1256,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     constexpr int LAST = PL::npass() - 1;
     constexpr int IN_ROW = C2R ? M + 1 : M;          // row lengths in complex values
     constexpr int RSTR = RC ? M + M / 16 : IN_ROW;   // smem row stride (RC: rows T banks apart, see k_c2c_pipe)
+    static_assert(!RC || RSTR <= padded_size<PADQ>(M), "padded rows must fit the stage buffer (sized for the scratch)");
     constexpr size_t BUF = real_pipe_buf_bytes<R, PL, PADQ, X, C2R>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
@@ -1757,6 +1759,17 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
 }
 
 
+// Hermitian step, shared-memory half: park the upper half of the core's outputs (elements >= M/2) at the UNPADDED
+// index M - k', i.e. at the bin index of the thread that pairs it with its own register value Z[k] (see k_real_pipe).
+template <typename R, class PL, int LAST>
+__device__ __forceinline__ void park_upper_half(const cx<R> (&x)[PL::E], cx<R> *park, int tid) {
+    static_for<PL::E>([&](auto S_) {
+        CIDX(slot, S_);
+        constexpr int e = out_elem<PL, LAST>(slot);
+        if constexpr (e >= PL::E / 2) park[PL::N - e * PL::T - tid] = x[slot];
+    });
+}
+
 // ----------------------------------------------------------------------------------------
 // Batched STFT front-end: the reference's only batched caller is the spectrogram loop
 // of playground/src/spectrogram.js:281-360 -- per frame: slice `window` samples at `frame*hop`,
@@ -1783,8 +1796,16 @@ enum { STFT_MODE_DB = 0, STFT_MODE_COMPLEX = 1 };
 __device__ __forceinline__ float stft_db(float re, float im, const StftParams &sp) {
     // computeMagnitude + magnitudeToDb + normalisation (spectrogram.js:78-96, :343-352)
     // 20*log10(v) = 6.0206*log2(v): one MUFU.LG2 instead of the ~25-instruction log10f (|error| < 1e-5 dB)
-    const float mag = sqrtf(re * re + im * im);
-    const float db = 6.0205999132796239f * __log2f(mag * sp.inv_half_n + 1e-10f);
+    float db;
+    if (sp.db_floor < -150.0f) {                       // (uniform) a floor this deep sees the reference's +1e-10 epsilon
+        const float mag = sqrtf(re * re + im * im);
+        db = 6.0205999132796239f * __log2f(mag * sp.inv_half_n + 1e-10f);
+    } else {
+        // 20 log10(m + 1e-10) = 10 log10(m^2) to 1e-6 dB wherever it exceeds -150 dB, and everything below the
+        // floor clamps to 0 either way: no square root, half the instructions of the exact form
+        const float p = fmaf(re, re, im * im) * (sp.inv_half_n * sp.inv_half_n);
+        db = 3.0102999566398120f * __log2f(fmaxf(p, 1e-20f));
+    }
     const float v = (db - sp.db_floor) * sp.inv_range;
     return fminf(1.0f, fmaxf(0.0f, v));
 }
@@ -1826,12 +1847,13 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
     }
     run_all<R, PL, PADQ, X, false>(x, tw, GTw<R>{nullptr, tw}, sm, tid, xi, false);
     if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
-    spill_outputs<R, PL, LAST, PADQ>(x, sm, tid);
+    park_upper_half<R, PL, LAST>(x, sm, tid);
     sync_transform<PL::T, X>(xi);
     if (!active) return;
 
     constexpr int HALF = M / 2;
-    constexpr int PER = (HALF + PL::T - 1) / PL::T;
+    constexpr int PER = PL::E / 2;
+    static_assert(PER * PL::T == HALF, "bins per thread");
     float *odb = reinterpret_cast<float *>(sp.out) + frame * (M + 1);
     float2 *ocx = reinterpret_cast<float2 *>(sp.out) + frame * (M + 1);
     auto emit = [&](int k, cx<R> v) {
@@ -1841,20 +1863,18 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
     static_for<PER>([&](auto I_) {
         CIDX(i, I_);
         const int k = tid + i * PL::T;
-        if (k < HALF) {
-            if (i == 0 && k == 0) {
-                const cx<R> z0 = sm[0];
-                emit(0, mk<R>(z0.x + z0.y, 0.0f));
-                emit(M, mk<R>(z0.x - z0.y, 0.0f));
-                emit(HALF, RealPost<R>::middle(sm[pad_idx<PADQ>(HALF)], ld_tw(rtw + HALF), M));
-            } else {
-                const cx<R> z = sm[pad_idx<PADQ>(k)], zm = sm[pad_idx<PADQ>(M - k)];
-                cx<R> xk, xm;
-                const twd<R> w = ld_tw(rtw + k);
-                RealPost<R>::pair(z, zm, w, w, xk, xm);
-                emit(k, xk);
-                emit(M - k, xm);
-            }
+        const cx<R> z = x[slot_of_elem<PL, LAST>(i)];                 // Z[k]: this thread's own output
+        if (i == 0 && k == 0) {
+            emit(0, mk<R>(z.x + z.y, 0.0f));
+            emit(M, mk<R>(z.x - z.y, 0.0f));
+            emit(HALF, RealPost<R>::middle(sm[HALF], ld_tw(rtw + HALF), M));
+        } else {
+            const cx<R> zm = sm[k];
+            cx<R> xk, xm;
+            const twd<R> w = ld_tw(rtw + k);
+            RealPost<R>::pair(z, zm, w, w, xk, xm);
+            emit(k, xk);
+            emit(M - k, xm);
         }
     });
 }
@@ -1871,6 +1891,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
     constexpr int M = PL::N;
     constexpr int LAST = PL::npass() - 1;
     constexpr int RSTR = M + M / 16;                   // smem row stride (float2): rows T banks apart
+    static_assert(RSTR <= padded_size<PADQ>(M), "the padded frame rows must fit the stage buffer (sized for the scratch)");
     constexpr size_t BUF = real_pipe_buf_bytes<R, PL, PADQ, X, false>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
@@ -1929,11 +1950,12 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
         __syncthreads();                               // raw rows and padded scratch alias
         run_all<R, PL, PADQ, X, false>(x, tw, GTw<R>{nullptr, tw}, scratch, tid, xi, false);
         if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
-        spill_outputs<R, PL, LAST, PADQ>(x, scratch, tid);
+        park_upper_half<R, PL, LAST>(x, scratch, tid);
         sync_transform<PL::T, X>(xi);
         if (active) {
             constexpr int HALF = M / 2;
-            constexpr int PER = (HALF + PL::T - 1) / PL::T;
+            constexpr int PER = PL::E / 2;
+            static_assert(PER * PL::T == HALF, "bins per thread");
             float *odb = reinterpret_cast<float *>(sp.out) + frame * (M + 1);
             float2 *ocx = reinterpret_cast<float2 *>(sp.out) + frame * (M + 1);
             auto emit = [&](int k, cx<R> v) {
@@ -1943,20 +1965,18 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
             static_for<PER>([&](auto I_) {
                 CIDX(i, I_);
                 const int k = tid + i * PL::T;
-                if (k < HALF) {
-                    if (i == 0 && k == 0) {
-                        const cx<R> z0 = scratch[0];
-                        emit(0, mk<R>(z0.x + z0.y, 0.0f));
-                        emit(M, mk<R>(z0.x - z0.y, 0.0f));
-                        emit(HALF, RealPost<R>::middle(scratch[pad_idx<PADQ>(HALF)], ld_tw(rtw + HALF), M));
-                    } else {
-                        const cx<R> z = scratch[pad_idx<PADQ>(k)], zm = scratch[pad_idx<PADQ>(M - k)];
-                        cx<R> xk, xm;
-                        const twd<R> w = ld_tw(rtw + k);
-                        RealPost<R>::pair(z, zm, w, w, xk, xm);
-                        emit(k, xk);
-                        emit(M - k, xm);
-                    }
+                const cx<R> z = x[slot_of_elem<PL, LAST>(i)];         // Z[k]: this thread's own output
+                if (i == 0 && k == 0) {
+                    emit(0, mk<R>(z.x + z.y, 0.0f));
+                    emit(M, mk<R>(z.x - z.y, 0.0f));
+                    emit(HALF, RealPost<R>::middle(scratch[HALF], ld_tw(rtw + HALF), M));
+                } else {
+                    const cx<R> zm = scratch[k];
+                    cx<R> xk, xm;
+                    const twd<R> w = ld_tw(rtw + k);
+                    RealPost<R>::pair(z, zm, w, w, xk, xm);
+                    emit(k, xk);
+                    emit(M - k, xm);
                 }
             });
         }

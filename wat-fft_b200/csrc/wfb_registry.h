@@ -177,16 +177,16 @@ struct StftVariant { const char *name; int core_n; std::vector<int> radices; stf
 cudaError_t launch_persistent_raw(const void *kernel, size_t smem, int threads, long work_items, void *params, cudaStream_t s);
 cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long ctas, void *params, cudaStream_t s);
 const std::vector<StftVariant> &variants_stft();
-template <class PL, int X, int MINB> struct StftLaunchers {
-    static constexpr size_t smem = sizeof(cx<float>) * (size_t)padded_size<PADQ>(PL::N) * X;
+template <class PL, int X, int MINB, int PQ = PADQ> struct StftLaunchers {
+    static constexpr size_t smem = sizeof(cx<float>) * (size_t)padded_size<PQ>(PL::N) * X;
     static cudaError_t launch(const StftParams &sp, cudaStream_t s) {
-        return launch_grid_raw((const void *)k_stft<PL, X, PADQ, MINB>, smem, PL::T * X, (sp.frames + X - 1) / X, (void *)&sp, s);
+        return launch_grid_raw((const void *)k_stft<PL, X, PQ, MINB>, smem, PL::T * X, (sp.frames + X - 1) / X, (void *)&sp, s);
     }
     // pipelined variant: XP frames per CTA (>= one warp of threads)
     static constexpr int XP = (PL::T * X >= 128) ? X : 128 / PL::T;
-    static constexpr size_t smem_pipe = 2 * real_pipe_buf_bytes<float, PL, PADQ, XP, false>() + 64;
+    static constexpr size_t smem_pipe = 2 * real_pipe_buf_bytes<float, PL, PQ, XP, false>() + 64;
     static cudaError_t launch_pipe(const StftParams &sp, cudaStream_t s) {
-        return launch_persistent_raw((const void *)k_stft_pipe<PL, XP, PADQ, MINB>, smem_pipe, PL::T * XP, (sp.frames + XP - 1) / XP, (void *)&sp, s);
+        return launch_persistent_raw((const void *)k_stft_pipe<PL, XP, PQ, MINB>, smem_pipe, PL::T * XP, (sp.frames + XP - 1) / XP, (void *)&sp, s);
     }
     static StftVariant make(const char *name) { return StftVariant{name, PL::N, plan_radices<PL>(), &launch, &launch_pipe}; }
 };

@@ -6,6 +6,8 @@ namespace wfb {
 #define V(PL) StftLaunchers<PL, XS(PL::T), 2>::make(#PL "_stft")
 const std::vector<StftVariant> &variants_stft() {
     static const std::vector<StftVariant> v = {
+        // (the one-exchange P32 cores of the plain r2c kernels were measured here too: no gain -- this kernel is bound by
+        //  the frame gather out of L2 and the per-bin dB arithmetic, not by the exchanges)
         V(F32_32), V(F32_64), V(F32_128), V(F32_256), V(F32_512), V(F32_1024), V(F32_2048), V(F32_4096),
     };
     return v;
