@@ -70,6 +70,24 @@ def test_gpu_spectrogram_matches_reference_loop(wf, oracle, n_fft, hop, window, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_fft,hop,zp", [(256, 64, 1), (1024, 256, 2)])
+def test_gpu_spectrogram_deep_floor_uses_exact_db(wf, oracle, n_fft, hop, zp):
+    """A floor below -150 dB sees the reference's +1e-10 epsilon (spectrogram.js:60-62): the kernel switches from the
+    fast 10*log10(|X|^2) form to the exact 20*log10(|X|/(N/2) + 1e-10) one.  A signal with exact zeros exercises it."""
+    x = _signal(6 * n_fft, seed=7)
+    x[: 2 * n_fft] = 0.0                                   # silent frames: magnitude 0 -> -200 dB
+    ref = om.spectrogram_reference(x, n_fft, hop, "hann", zp, gain=0.0, range_db=220.0, rfft=oracle.rfft_split_f32)
+    got = wf.generateSpectrogram(x, 16000.0, n_fft, hop, "hann", zp, gain=0.0, range=220.0)
+    g = got["data"].reshape(ref.shape)
+    assert abs(float(g[0, 5]) - (220.0 - 200.0) / 220.0) < 1e-4      # silence sits on the epsilon, not on the floor
+    assert np.max(np.abs(g - ref)) < 2e-4, np.max(np.abs(g - ref))
+    # and the fast path (floor at -70 dB) agrees with the same reference loop on the same signal
+    ref2 = om.spectrogram_reference(x, n_fft, hop, "hann", zp, gain=0.0, range_db=70.0, rfft=oracle.rfft_split_f32)
+    got2 = wf.generateSpectrogram(x, 16000.0, n_fft, hop, "hann", zp, gain=0.0, range=70.0)
+    assert np.max(np.abs(got2["data"].reshape(ref2.shape) - ref2)) < 2e-4
+
+
+@pytest.mark.gpu
 def test_gpu_spectrogram_errors_and_long_signal(wf, oracle):
     with pytest.raises(ValueError):
         wf.generateSpectrogram(np.zeros(100, np.float32), 16000.0, 1024, 256)

@@ -24,6 +24,17 @@ for spec in specs:
     parts = spec.split(":")
     kind, n = parts[0], int(parts[1])
     variant = int(parts[2]) if len(parts) > 2 else 0
+    if kind == "stft":                                  # stft:N  (WFB_STFT_PIPE_MIN_N selects the pipelined kernel)
+        ns = 1 << 26
+        sp = wf.Spectrogram(ns, n, n // 4, "hann", 1, flags=C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+        x = torch.rand(ns, device=dev) * 2 - 1
+        out = torch.empty(sp.numFrames * sp.numBins, device=dev)
+        for _ in range(3):
+            sp.run_device(x.data_ptr(), out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        print("ran", spec, "frames", sp.numFrames, flush=True)
+        sp.dispose()
+        continue
     f64 = kind.endswith("f64")
     e = 8 if f64 else 4
     dt = torch.float64 if f64 else torch.float32

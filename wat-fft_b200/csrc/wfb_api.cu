@@ -697,6 +697,9 @@ int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void
     sp.frames = st->frames; sp.hop = st->hop; sp.wsize = st->wsize; sp.mode = st->mode & 0xFF;
     sp.db_floor = st->db_floor; sp.inv_range = st->inv_range; sp.inv_half_n = 2.0f / (float)st->fft_size;
     sp.ctr = nullptr;
+    // fast dB path: v = lg_a * log2(|2 X|^2) + lg_b  ==  (10 log10(|X|^2 c^2) - floor) / range,  c = 2 / fft_size
+    sp.lg_a = 3.0102999566398120f * st->inv_range;
+    sp.lg_b = sp.lg_a * (2.0f * log2f(sp.inv_half_n) - 2.0f) - st->db_floor * st->inv_range;
     // frames are TMA-copyable when their starts are 16-byte aligned (hop % 4 == 0, aligned base)
     static const int pipe_min = [] { const char *e = getenv("WFB_STFT_PIPE_MIN_N"); return e ? atoi(e) : 8192; }();
     const bool pipe = st->fft_size >= pipe_min && st->hop % 4 == 0 && st->wsize % 4 == 0 && ((uintptr_t)d_samples % 16) == 0;

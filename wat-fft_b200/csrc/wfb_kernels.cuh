@@ -1790,28 +1790,76 @@ struct StftParams {
     float inv_range;           // 1 / range
     float inv_half_n;          // 1 / (N/2)
     unsigned long long *ctr;   // pipelined kernel: zeroed tile counter of this launch
+    float lg_a, lg_b;          // fast dB path: value = lg_a * log2(|2 X|^2) + lg_b (host-folded constants)
 };
 enum { STFT_MODE_DB = 0, STFT_MODE_COMPLEX = 1 };
+// kernel flavours (template parameter KM): the dB output has a fast path that needs no square root and folds every
+// constant of computeMagnitude / magnitudeToDb / the gain-range normalisation into one FFMA after the MUFU.LG2:
+//   20 log10(|X| c + 1e-10) = 10 log10(|X|^2 c^2) to 1e-6 dB wherever the result is above -150 dB, and everything below
+//   the floor (gain - range) clamps to 0 either way; a floor deeper than -150 dB selects the exact form.
+enum { STFT_K_FAST = 0, STFT_K_EXACT = 1, STFT_K_COMPLEX = 2 };
 
 __device__ __forceinline__ float stft_db(float re, float im, const StftParams &sp) {
     // computeMagnitude + magnitudeToDb + normalisation (spectrogram.js:78-96, :343-352)
     // 20*log10(v) = 6.0206*log2(v): one MUFU.LG2 instead of the ~25-instruction log10f (|error| < 1e-5 dB)
-    float db;
-    if (sp.db_floor < -150.0f) {                       // (uniform) a floor this deep sees the reference's +1e-10 epsilon
-        const float mag = sqrtf(re * re + im * im);
-        db = 6.0205999132796239f * __log2f(mag * sp.inv_half_n + 1e-10f);
-    } else {
-        // 20 log10(m + 1e-10) = 10 log10(m^2) to 1e-6 dB wherever it exceeds -150 dB, and everything below the
-        // floor clamps to 0 either way: no square root, half the instructions of the exact form
-        const float p = fmaf(re, re, im * im) * (sp.inv_half_n * sp.inv_half_n);
-        db = 3.0102999566398120f * __log2f(fmaxf(p, 1e-20f));
-    }
+    const float mag = sqrtf(re * re + im * im);
+    const float db = 6.0205999132796239f * __log2f(mag * sp.inv_half_n + 1e-10f);
     const float v = (db - sp.db_floor) * sp.inv_range;
     return fminf(1.0f, fmaxf(0.0f, v));
 }
+// fast path on the UNHALVED bin value 2 X[k] (the 1/2 of the Hermitian step is folded into lg_b as well)
+__device__ __forceinline__ float stft_db_fast(cx<float> x2, const StftParams &sp) {
+    const float v = fmaf(__log2f(fmaf(x2.x, x2.x, x2.y * x2.y)), sp.lg_a, sp.lg_b);   // log2(0) = -inf clamps to 0
+    return fminf(1.0f, fmaxf(0.0f, v));
+}
 
-template <class PL, int X, int PADQ, int MINB>
-__global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
+// Hermitian post-process + output stage shared by the two STFT kernels.  `park` holds the upper half of the core's
+// outputs (park_upper_half); Z[k] for k < M/2 is the thread's own register value.
+template <class PL, int LAST, int KM>
+__device__ __forceinline__ void stft_post(const cx<float> (&x)[PL::E], const cx<float> *park, const float2 *rtw, int tid,
+                                          long frame, const StftParams &sp) {
+    using R = float;
+    constexpr int M = PL::N, HALF = M / 2, PER = PL::E / 2;
+    static_assert(PER * PL::T == HALF, "bins per thread");
+    float *odb = reinterpret_cast<float *>(sp.out) + frame * (M + 1);
+    float2 *ocx = reinterpret_cast<float2 *>(sp.out) + frame * (M + 1);
+    auto emit = [&](int k, cx<R> v) {                                   // exact forms (and the three special bins)
+        if constexpr (KM == STFT_K_COMPLEX) st_stream(ocx + k, make_float2(v.x, v.y));
+        else st_stream(odb + k, k < 3 ? 0.0f : stft_db(v.x, v.y, sp));  // DC and near-DC bins zeroed (:338-342)
+    };
+    static_for<PER>([&](auto I_) {
+        CIDX(i, I_);
+        const int k = tid + i * PL::T;
+        const cx<R> z = x[slot_of_elem<PL, LAST>(i)];                   // Z[k]: this thread's own output
+        if (i == 0 && k == 0) {
+            emit(0, mk<R>(z.x + z.y, 0.0f));
+            emit(M, mk<R>(z.x - z.y, 0.0f));
+            emit(HALF, RealPost<R>::middle(park[HALF], ld_tw(rtw + HALF), M));
+        } else {
+            const cx<R> zm = park[k];
+            const twd<R> w = ld_tw(rtw + k);
+            if constexpr (KM == STFT_K_FAST) {
+                // 2 X[k] and 2 X[M-k]: RealPost::pair without its four multiplications by 1/2
+                const R gr = z.x + zm.x, gi = z.y - zm.y, hr = z.y + zm.y, hi = zm.x - z.x;
+                const R tr = fmaf(w.ny, hi, w.x * hr), ti = fmaf(w.y, hr, w.x * hi);
+                float vk = stft_db_fast(mk<R>(gr + tr, gi + ti), sp);
+                const float vm = stft_db_fast(mk<R>(gr - tr, ti - gi), sp);
+                if constexpr (i * PL::T < 3) vk = k < 3 ? 0.0f : vk;    // only the first block(s) hold bins below 3
+                st_stream(odb + k, vk);
+                st_stream(odb + (M - k), vm);
+            } else {
+                cx<R> xk, xm;
+                RealPost<R>::pair(z, zm, w, w, xk, xm);
+                emit(k, xk);
+                emit(M - k, xm);
+            }
+        }
+    });
+}
+
+// KM: output flavour (STFT_K_*); PAD: window shorter than the FFT size (zero padding)
+template <class PL, int X, int PADQ, int MINB, int KM, bool PAD>
+__global__ void __launch_bounds__(PL::T *X, MINB) k_stft(const __grid_constant__ StftParams sp) {
     static_assert(PL::valid(), "plan does not factor N");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using R = float;
@@ -1833,7 +1881,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
             const int i0 = 2 * (tid + e * PL::T);
             float a = 0.0f, b = 0.0f;
             if (vec) {
-                if (active && i0 < sp.wsize) {
+                if (!PAD || i0 < sp.wsize) {           // (an inactive group reads frame 0 and stores nothing)
                     const float2 v = __ldg(reinterpret_cast<const float2 *>(s + i0));
                     const float2 w = __ldg(reinterpret_cast<const float2 *>(sp.window + i0));
                     a = v.x * w.x; b = v.y * w.y;
@@ -1851,40 +1899,15 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(StftParams sp) {
     sync_transform<PL::T, X>(xi);
     if (!active) return;
 
-    constexpr int HALF = M / 2;
-    constexpr int PER = PL::E / 2;
-    static_assert(PER * PL::T == HALF, "bins per thread");
-    float *odb = reinterpret_cast<float *>(sp.out) + frame * (M + 1);
-    float2 *ocx = reinterpret_cast<float2 *>(sp.out) + frame * (M + 1);
-    auto emit = [&](int k, cx<R> v) {
-        if (sp.mode == STFT_MODE_COMPLEX) st_stream(ocx + k, make_float2(v.x, v.y));
-        else st_stream(odb + k, k < 3 ? 0.0f : stft_db(v.x, v.y, sp));      // DC and near-DC bins zeroed (:338-342)
-    };
-    static_for<PER>([&](auto I_) {
-        CIDX(i, I_);
-        const int k = tid + i * PL::T;
-        const cx<R> z = x[slot_of_elem<PL, LAST>(i)];                 // Z[k]: this thread's own output
-        if (i == 0 && k == 0) {
-            emit(0, mk<R>(z.x + z.y, 0.0f));
-            emit(M, mk<R>(z.x - z.y, 0.0f));
-            emit(HALF, RealPost<R>::middle(sm[HALF], ld_tw(rtw + HALF), M));
-        } else {
-            const cx<R> zm = sm[k];
-            cx<R> xk, xm;
-            const twd<R> w = ld_tw(rtw + k);
-            RealPost<R>::pair(z, zm, w, w, xk, xm);
-            emit(k, xk);
-            emit(M - k, xm);
-        }
-    });
+    stft_post<PL, LAST, KM>(x, sm, rtw, tid, frame, sp);
 }
 
 
 // TMA-pipelined STFT: frames are rows at `hop` stride in the sample array, so when hop is a
 // multiple of 4 samples (16-byte aligned frame starts) each frame is one bulk copy into a padded
 // smem row, prefetched one tile ahead exactly like k_real_pipe's row-copy mode.
-template <class PL, int X, int PADQ, int MINB>
-__global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
+template <class PL, int X, int PADQ, int MINB, int KM, bool PAD>
+__global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(const __grid_constant__ StftParams sp) {
     static_assert(PL::valid() && PL::T * X >= 32, "needs a full issuing warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using R = float;
@@ -1941,7 +1964,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
             CIDX(e, E_);
             const int pidx = tid + e * PL::T;
             float a = 0.0f, b = 0.0f;
-            if (active && 2 * pidx < sp.wsize) {
+            if (!PAD || 2 * pidx < sp.wsize) {         // (rows beyond the last frame hold stale data and store nothing)
                 const float2 v = raw[pidx], w = __ldg(win + pidx);
                 a = v.x * w.x; b = v.y * w.y;
             }
@@ -1952,34 +1975,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(StftParams sp) {
         if (PL::npass() > 1) sync_transform<PL::T, X>(xi);
         park_upper_half<R, PL, LAST>(x, scratch, tid);
         sync_transform<PL::T, X>(xi);
-        if (active) {
-            constexpr int HALF = M / 2;
-            constexpr int PER = PL::E / 2;
-            static_assert(PER * PL::T == HALF, "bins per thread");
-            float *odb = reinterpret_cast<float *>(sp.out) + frame * (M + 1);
-            float2 *ocx = reinterpret_cast<float2 *>(sp.out) + frame * (M + 1);
-            auto emit = [&](int k, cx<R> v) {
-                if (sp.mode == STFT_MODE_COMPLEX) st_stream(ocx + k, make_float2(v.x, v.y));
-                else st_stream(odb + k, k < 3 ? 0.0f : stft_db(v.x, v.y, sp));
-            };
-            static_for<PER>([&](auto I_) {
-                CIDX(i, I_);
-                const int k = tid + i * PL::T;
-                const cx<R> z = x[slot_of_elem<PL, LAST>(i)];         // Z[k]: this thread's own output
-                if (i == 0 && k == 0) {
-                    emit(0, mk<R>(z.x + z.y, 0.0f));
-                    emit(M, mk<R>(z.x - z.y, 0.0f));
-                    emit(HALF, RealPost<R>::middle(scratch[HALF], ld_tw(rtw + HALF), M));
-                } else {
-                    const cx<R> zm = scratch[k];
-                    cx<R> xk, xm;
-                    const twd<R> w = ld_tw(rtw + k);
-                    RealPost<R>::pair(z, zm, w, w, xk, xm);
-                    emit(k, xk);
-                    emit(M - k, xm);
-                }
-            });
-        }
+        if (active) stft_post<PL, LAST, KM>(x, scratch, rtw, tid, frame, sp);
     }
 }
 

@@ -179,14 +179,34 @@ cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long c
 const std::vector<StftVariant> &variants_stft();
 template <class PL, int X, int MINB, int PQ = PADQ> struct StftLaunchers {
     static constexpr size_t smem = sizeof(cx<float>) * (size_t)padded_size<PQ>(PL::N) * X;
+    // kernel flavour: fast dB (floor above -150 dB) / exact dB / complex output; the unpadded fast-dB case (window =
+    // FFT size, the spectrogram default) gets its own instantiation without the per-element bound check
+    static int flavour(const StftParams &sp) {
+        if (sp.mode == STFT_MODE_COMPLEX) return STFT_K_COMPLEX;
+        return sp.db_floor >= -150.0f ? STFT_K_FAST : STFT_K_EXACT;
+    }
     static cudaError_t launch(const StftParams &sp, cudaStream_t s) {
-        return launch_grid_raw((const void *)k_stft<PL, X, PQ, MINB>, smem, PL::T * X, (sp.frames + X - 1) / X, (void *)&sp, s);
+        const bool pad = sp.wsize < 2 * PL::N;
+        const void *k;
+        switch (flavour(sp)) {
+            case STFT_K_FAST: k = pad ? (const void *)k_stft<PL, X, PQ, MINB, STFT_K_FAST, true> : (const void *)k_stft<PL, X, PQ, MINB, STFT_K_FAST, false>; break;
+            case STFT_K_EXACT: k = (const void *)k_stft<PL, X, PQ, MINB, STFT_K_EXACT, true>; break;
+            default: k = (const void *)k_stft<PL, X, PQ, MINB, STFT_K_COMPLEX, true>; break;
+        }
+        return launch_grid_raw(k, smem, PL::T * X, (sp.frames + X - 1) / X, (void *)&sp, s);
     }
     // pipelined variant: XP frames per CTA (>= one warp of threads)
     static constexpr int XP = (PL::T * X >= 128) ? X : 128 / PL::T;
     static constexpr size_t smem_pipe = 2 * real_pipe_buf_bytes<float, PL, PQ, XP, false>() + 64;
     static cudaError_t launch_pipe(const StftParams &sp, cudaStream_t s) {
-        return launch_persistent_raw((const void *)k_stft_pipe<PL, XP, PQ, MINB>, smem_pipe, PL::T * XP, (sp.frames + XP - 1) / XP, (void *)&sp, s);
+        const bool pad = sp.wsize < 2 * PL::N;
+        const void *k;
+        switch (flavour(sp)) {
+            case STFT_K_FAST: k = pad ? (const void *)k_stft_pipe<PL, XP, PQ, MINB, STFT_K_FAST, true> : (const void *)k_stft_pipe<PL, XP, PQ, MINB, STFT_K_FAST, false>; break;
+            case STFT_K_EXACT: k = (const void *)k_stft_pipe<PL, XP, PQ, MINB, STFT_K_EXACT, true>; break;
+            default: k = (const void *)k_stft_pipe<PL, XP, PQ, MINB, STFT_K_COMPLEX, true>; break;
+        }
+        return launch_persistent_raw(k, smem_pipe, PL::T * XP, (sp.frames + XP - 1) / XP, (void *)&sp, s);
     }
     static StftVariant make(const char *name) { return StftVariant{name, PL::N, plan_radices<PL>(), &launch, &launch_pipe}; }
 };
