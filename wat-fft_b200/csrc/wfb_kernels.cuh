@@ -1094,33 +1094,34 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
 //     drain their own store group (cp.async.bulk.wait_group.read) right before the refill -- after the row
 //     loads of the current tile, which gives the store engine that time for free.
 // ----------------------------------------------------------------------------------------
-template <class PL, int IO> __host__ __device__ constexpr int tpipe_group() {
-    const int row_bytes = (IO == IO_SPLIT ? 4 : 8) * PL::N;           // bytes of one row in one plane
+template <typename R, class PL, int IO> __host__ __device__ constexpr int tpipe_group() {
+    const int row_bytes = (IO == IO_SPLIT ? 1 : 2) * (int)sizeof(R) * PL::N;   // bytes of one row in one plane
     return row_bytes >= 512 ? 1 : 512 / row_bytes;
 }
-template <class PL, int X, int IO> __host__ __device__ constexpr size_t tpipe_buf_bytes() {
-    constexpr int G = tpipe_group<PL, IO>();
-    return ((size_t)(G * 8 * PL::N + 16) * (X / G) + 127) / 128 * 128;
+template <typename R, class PL, int X, int IO> __host__ __device__ constexpr size_t tpipe_buf_bytes() {
+    constexpr int G = tpipe_group<R, PL, IO>();
+    return ((size_t)(G * 2 * sizeof(R) * PL::N + 16) * (X / G) + 127) / 128 * 128;
 }
 
-template <class PL, int X, int IO, bool INV, int MINB>
+template <typename R, class PL, int X, int IO, bool INV, int MINB>
 __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 32 == 0, "tile kernel: one thread per row, whole warps");
+    static_assert(RT<R>::LANES == 1 && (sizeof(R) == 4 || IO == IO_INTERLEAVED), "f32 (both layouts) or f64 interleaved");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using R = float;
     constexpr int N = PL::N;
-    constexpr int G = tpipe_group<PL, IO>();           // rows per bulk copy
+    constexpr int ES = (int)sizeof(R);                 // bytes of a real
+    constexpr int G = tpipe_group<R, PL, IO>();        // rows per bulk copy
     constexpr int NG = X / G;                          // groups per tile
     static_assert(X % G == 0 && NG % 8 == 0, "8 consecutive lanes must sit in 8 consecutive groups");
-    constexpr int GSTR = G * 8 * N + 16;               // group stride, bytes (odd multiple of 16)
-    constexpr int PLANE = (IO == IO_SPLIT ? 4 : 8) * N; // bytes of one row in one plane
-    constexpr size_t BUF = tpipe_buf_bytes<PL, X, IO>();
+    constexpr int GSTR = G * 2 * ES * N + 16;          // group stride, bytes (odd multiple of 16)
+    constexpr int PLANE = (IO == IO_SPLIT ? 1 : 2) * ES * N;   // bytes of one row in one plane
+    constexpr size_t BUF = tpipe_buf_bytes<R, PL, X, IO>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);
     const int t = threadIdx.x;
     const int gj = t % NG, gb = t / NG;                // my group, my row within it
     const long tiles = (p.batch + X - 1) / X;
-    const float2 *tw = reinterpret_cast<const float2 *>(p.tw);
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
     auto cta_sync = [&]() { if constexpr (X == 32) __syncwarp(); else __syncthreads(); };
 
     if (t == 0) {
@@ -1135,17 +1136,17 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
         const int rows = tile_rows(tile);
         unsigned char *buf = smem_raw + st * BUF;
         bulk_wait_read_all();                          // this lane's stores out of this stage have left shared memory
-        if (t == 0) mbar_expect_tx(mbar + st, (uint32_t)(rows * 8 * N));
+        if (t == 0) mbar_expect_tx(mbar + st, (uint32_t)(rows * 2 * ES * N));
         __syncwarp();
         for (int g = t; g * G < rows; g += 32) {
             const long row = tile * X + (long)g * G;
             const int nr = rows - g * G < G ? rows - g * G : G;
             unsigned char *dst = buf + (size_t)g * GSTR;
             if constexpr (IO == IO_SPLIT) {
-                tma_load_1d(dst, reinterpret_cast<const float *>(p.in0) + row * N, (uint32_t)(nr * PLANE), mbar + st);
-                tma_load_1d(dst + G * PLANE, reinterpret_cast<const float *>(p.in1) + row * N, (uint32_t)(nr * PLANE), mbar + st);
+                tma_load_1d(dst, reinterpret_cast<const R *>(p.in0) + row * N, (uint32_t)(nr * PLANE), mbar + st);
+                tma_load_1d(dst + G * PLANE, reinterpret_cast<const R *>(p.in1) + row * N, (uint32_t)(nr * PLANE), mbar + st);
             } else {
-                tma_load_1d(dst, reinterpret_cast<const float *>(p.in0) + row * 2 * N, (uint32_t)(nr * PLANE), mbar + st);
+                tma_load_1d(dst, reinterpret_cast<const R *>(p.in0) + row * 2 * N, (uint32_t)(nr * PLANE), mbar + st);
             }
         }
     };
@@ -1174,6 +1175,9 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
                 x[4 * h] = mk<R>(a.x, b.x); x[4 * h + 1] = mk<R>(a.y, b.y);
                 x[4 * h + 2] = mk<R>(a.z, b.z); x[4 * h + 3] = mk<R>(a.w, b.w);
             });
+        } else if constexpr (sizeof(R) == 8) {
+            const double2 *rowd = reinterpret_cast<const double2 *>(rowp);
+            static_for<N>([&](auto H_) { CIDX(h, H_); const double2 v = rowd[h]; x[h] = mk<R>(v.x, v.y); });
         } else {
             static_for<N / 2>([&](auto H_) {
                 CIDX(h, H_);
@@ -1185,7 +1189,7 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
 
         run_pass<R, PL, 0, INV>(x, tw, UTw<R, PL>::make(p, tw), 0);
 
-        const float sc = INV ? (float)p.scale : 1.0f;
+        const R sc = INV ? (R)p.scale : R(1);
         if constexpr (IO == IO_SPLIT) {
             static_for<N / 4>([&](auto H_) {
                 CIDX(h, H_);
@@ -1194,6 +1198,15 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
                 float4 a = make_float4(x[s0].x, x[s1].x, x[s2].x, x[s3].x), b = make_float4(x[s0].y, x[s1].y, x[s2].y, x[s3].y);
                 if (INV) { a = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc); b = make_float4(b.x * sc, b.y * sc, b.z * sc, b.w * sc); }
                 rowp[h] = a; rowq[h] = b;
+            });
+        } else if constexpr (sizeof(R) == 8) {
+            double2 *rowd = reinterpret_cast<double2 *>(rowp);
+            static_for<N>([&](auto H_) {
+                CIDX(h, H_);
+                constexpr int s0 = slot_of_elem<PL, 0>(h);
+                double2 v = make_double2(x[s0].x, x[s0].y);
+                if (INV) v = make_double2(v.x * sc, v.y * sc);
+                rowd[h] = v;
             });
         } else {
             static_for<N / 2>([&](auto H_) {
@@ -1212,10 +1225,10 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
                 const int nr = rows - g * G < G ? rows - g * G : G;
                 const unsigned char *src = buf + (size_t)g * GSTR;
                 if constexpr (IO == IO_SPLIT) {
-                    tma_store_1d(reinterpret_cast<float *>(p.out0) + row * N, src, (uint32_t)(nr * PLANE));
-                    tma_store_1d(reinterpret_cast<float *>(p.out1) + row * N, src + G * PLANE, (uint32_t)(nr * PLANE));
+                    tma_store_1d(reinterpret_cast<R *>(p.out0) + row * N, src, (uint32_t)(nr * PLANE));
+                    tma_store_1d(reinterpret_cast<R *>(p.out1) + row * N, src + G * PLANE, (uint32_t)(nr * PLANE));
                 } else {
-                    tma_store_1d(reinterpret_cast<float *>(p.out0) + row * 2 * N, src, (uint32_t)(nr * PLANE));
+                    tma_store_1d(reinterpret_cast<R *>(p.out0) + row * 2 * N, src, (uint32_t)(nr * PLANE));
                 }
             }
             bulk_commit();
@@ -1604,35 +1617,46 @@ __global__ void __launch_bounds__(X, MINB) k_c2r_tile(const __grid_constant__ KP
 // (LDS.64 on the dense side, odd row stride): both sides are conflict-free.  A ragged last tile (fewer than X
 // rows) moves its spectrum rows with plain loads/stores (bulk copies need 16-byte sizes).
 // ----------------------------------------------------------------------------------------
-template <class PL> __host__ __device__ constexpr int rtpipe_group() { return 8 * PL::N >= 512 ? 1 : 512 / (8 * PL::N); }
-template <class PL, int X> __host__ __device__ constexpr size_t rtpipe_buf_bytes() {
-    constexpr int G = rtpipe_group<PL>();
-    size_t padded = (size_t)(G * 8 * PL::N + 16) * (X / G), dense = (size_t)X * (PL::N + 1) * 8;
+template <typename R, class PL> __host__ __device__ constexpr int rtpipe_group() {
+    const int row_bytes = 2 * (int)sizeof(R) * PL::N;                  // a time-domain row: N = 2M reals
+    return row_bytes >= 512 ? 1 : 512 / row_bytes;
+}
+template <typename R, class PL, int X> __host__ __device__ constexpr size_t rtpipe_buf_bytes() {
+    constexpr int G = rtpipe_group<R, PL>();
+    size_t padded = (size_t)(G * 2 * sizeof(R) * PL::N + 16) * (X / G), dense = (size_t)X * (PL::N + 1) * 2 * sizeof(R);
     return ((padded > dense ? padded : dense) + 127) / 128 * 128;
 }
 
-template <class PL, int X, bool C2R, int MINB>
+template <typename R, class PL, int X, bool C2R, int MINB>
 __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && PL::T == 1 && PL::npass() == 1 && X % 32 == 0, "tile kernel: one thread per row, whole warps");
+    static_assert(RT<R>::LANES == 1, "scalar lanes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using R = float;
+    using V2 = typename VecOf<R>::v2;                  // one complex value as stored (float2 / double2)
     constexpr int M = PL::N, N = 2 * M, HALF = M / 2;
-    constexpr int G = rtpipe_group<PL>();              // time-domain rows per bulk copy
-    static_assert(G <= 2 && X % (8 * G) == 0, "thread <-> row mapping covers G = 1, 2");
-    constexpr int ROWT = 4 * N;                        // bytes of a time-domain row
+    constexpr int ES = (int)sizeof(R);
+    constexpr int G = rtpipe_group<R, PL>();           // time-domain rows per bulk copy
+    static_assert((G <= 2 || (sizeof(R) == 8 && G <= 8)) && X % (8 * G) == 0, "thread <-> row mapping: f32 G = 1, 2; f64 G = 1..8");
+    constexpr int ROWT = ES * N;                       // bytes of a time-domain row
     constexpr int GSTR = G * ROWT + 16;                // group stride, bytes (odd multiple of 16)
-    constexpr size_t BUF = rtpipe_buf_bytes<PL, X>();
+    constexpr int SPECB = (M + 1) * 2 * ES;            // bytes of a spectrum row
+    constexpr size_t BUF = rtpipe_buf_bytes<R, PL, X>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     long *slot = reinterpret_cast<long *>(smem_raw + 2 * BUF + 32);
     const int t = threadIdx.x;
-    const int lane8 = t % (8 * G);
-    const int myrow = t - lane8 + G * (lane8 % 8) + lane8 / 8;      // my row of the tile
+    // my row of the tile.  f32 (8-byte bins: 16 lanes per shared-memory phase on the dense side): within 8G lanes,
+    // row = G*(lane % 8) + lane / 8.  f64 (16-byte bins: 8 lanes per phase on BOTH sides): the 8 lanes of a phase
+    // must sit in 8 distinct groups AND in 8 rows distinct mod 8: lane j of phase ph takes row
+    // G*j + (j / (8/G) + ph) mod G of its group -- for G = 2: rows 0,2,4,6,9,11,13,15 / 1,3,5,7,8,10,12,14.
+    const int lane8 = t % (8 * G), j8 = lane8 % 8;
+    const int myrow = t - lane8 + (ES == 8 ? G * j8 + (j8 / (8 / G) + lane8 / 8) % G : G * j8 + lane8 / 8);
     const long tiles = (p.batch + X - 1) / X;
-    const float2 *tw = reinterpret_cast<const float2 *>(p.tw);
-    const float2 *rtw = reinterpret_cast<const float2 *>(p.rtw);
-    float *time_g = C2R ? reinterpret_cast<float *>(p.out0) : const_cast<float *>(reinterpret_cast<const float *>(p.in0));
-    float2 *spec_g = C2R ? const_cast<float2 *>(reinterpret_cast<const float2 *>(p.in0)) : reinterpret_cast<float2 *>(p.out0);
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+    const typename RT<R>::twel *rtw = reinterpret_cast<const typename RT<R>::twel *>(p.rtw);
+    R *time_g = C2R ? reinterpret_cast<R *>(p.out0) : const_cast<R *>(reinterpret_cast<const R *>(p.in0));
+    V2 *spec_g = C2R ? const_cast<V2 *>(reinterpret_cast<const V2 *>(p.in0)) : reinterpret_cast<V2 *>(p.out0);
     auto cta_sync = [&]() { if constexpr (X == 32) __syncwarp(); else __syncthreads(); };
+    auto bulk_ok = [&](int rows) { return (rows * SPECB) % 16 == 0; };      // bulk copies move multiples of 16 bytes
 
     if (t == 0) {
         mbar_init(mbar + 0, 1);
@@ -1654,10 +1678,10 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
                 const int nr = rows - g * G < G ? rows - g * G : G;
                 tma_load_1d(buf + (size_t)g * GSTR, time_g + (tile * X + (long)g * G) * N, (uint32_t)(nr * ROWT), mbar + st);
             }
-        } else if (rows == X) {                        // ragged tiles are copied by the threads (see the main loop)
+        } else if (bulk_ok(rows)) {                    // otherwise the threads copy the tile (see the main loop)
             if (t == 0) {
-                mbar_expect_tx(mbar + st, (uint32_t)(X * (M + 1) * 8));
-                tma_load_1d(buf, spec_g + tile * X * (M + 1), (uint32_t)(X * (M + 1) * 8), mbar + st);
+                mbar_expect_tx(mbar + st, (uint32_t)(rows * SPECB));
+                tma_load_1d(buf, spec_g + tile * X * (M + 1), (uint32_t)(rows * SPECB), mbar + st);
             }
         }
     };
@@ -1673,77 +1697,88 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
         if (tile >= tiles) break;
         unsigned char *buf = smem_raw + st * BUF;
         const int rows = tile_rows(tile);
-        float2 *dense = reinterpret_cast<float2 *>(buf);
-        float2 *drow = dense + (size_t)myrow * (M + 1);                                   // my spectrum row
-        float4 *trow = reinterpret_cast<float4 *>(buf + (size_t)(myrow / G) * GSTR + (myrow % G) * ROWT);   // my time row
-        if (!C2R || rows == X) {
+        V2 *dense = reinterpret_cast<V2 *>(buf);
+        V2 *drow = dense + (size_t)myrow * (M + 1);                                       // my spectrum row
+        unsigned char *trow = buf + (size_t)(myrow / G) * GSTR + (myrow % G) * ROWT;      // my time row
+        if (!C2R || bulk_ok(rows)) {
             mbar_wait(mbar + st, (phasebits >> st) & 1u);
             phasebits ^= 1u << st;
         } else {
-            const float2 *src = spec_g + tile * X * (M + 1);
+            const V2 *src = spec_g + tile * X * (M + 1);
             for (int f = t; f < rows * (M + 1); f += X) dense[f] = ld_stream(src + f);
             cta_sync();
         }
 
         if constexpr (!C2R) {
-            static_for<M / 2>([&](auto H_) {
-                CIDX(h, H_);
-                const float4 v = trow[h];
-                x[2 * h] = mk<R>(v.x, v.y);            // z[j] = x[2j] + i x[2j+1]
-                x[2 * h + 1] = mk<R>(v.z, v.w);
-            });
+            if constexpr (ES == 8) {                   // z[j] = x[2j] + i x[2j+1]: one LDS.128 per complex value
+                const double2 *tr = reinterpret_cast<const double2 *>(trow);
+                static_for<M>([&](auto H_) { CIDX(h, H_); const double2 v = tr[h]; x[h] = mk<R>(v.x, v.y); });
+            } else {
+                const float4 *tr = reinterpret_cast<const float4 *>(trow);
+                static_for<M / 2>([&](auto H_) {
+                    CIDX(h, H_);
+                    const float4 v = tr[h];
+                    x[2 * h] = mk<R>(v.x, v.y);
+                    x[2 * h + 1] = mk<R>(v.z, v.w);
+                });
+            }
             claim_and_issue<true>(p.ctr, pending, tiles, slot, st ^ 1, issue);
             run_pass<R, PL, 0, false>(x, tw, UTw<R, PL>::make(p, tw), 0);
             cta_sync();                                // time rows and spectrum rows alias
+            auto put = [&](int k, cx<R> v) { V2 o; o.x = v.x; o.y = v.y; drow[k] = o; };
             const cx<R> z0 = x[slot_of_elem<PL, 0>(0)];
-            drow[0] = make_float2(z0.x + z0.y, 0.0f);
-            drow[M] = make_float2(z0.x - z0.y, 0.0f);
-            const cx<R> xh = RealPost<R>::middle(x[slot_of_elem<PL, 0>(HALF)], ld_tw(rtw + HALF), M);
-            drow[HALF] = make_float2(xh.x, xh.y);
+            put(0, mk<R>(radd(z0.x, z0.y), R(0)));
+            put(M, mk<R>(rsub(z0.x, z0.y), R(0)));
+            put(HALF, RealPost<R>::middle(x[slot_of_elem<PL, 0>(HALF)], ld_tw(rtw + HALF), M));
             static_for<HALF - 1>([&](auto K_) {
                 CIDX(k0, K_);
                 constexpr int k = k0 + 1;
                 const cx<R> z = x[slot_of_elem<PL, 0>(k)], zm = x[slot_of_elem<PL, 0>(M - k)];
                 cx<R> xk, xm;
-                const twd<R> w = ld_tw(rtw + k);
-                RealPost<R>::pair(z, zm, w, w, xk, xm);
-                drow[k] = make_float2(xk.x, xk.y);
-                drow[M - k] = make_float2(xm.x, xm.y);
+                RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);     // (f32 ignores the second table entry)
+                put(k, xk);
+                put(M - k, xm);
             });
-            if (rows == X) {
+            if (bulk_ok(rows)) {
                 fence_proxy_async();
                 cta_sync();
-                if (t == 0) { tma_store_1d(spec_g + tile * X * (M + 1), buf, (uint32_t)(X * (M + 1) * 8)); bulk_commit(); }
+                if (t == 0) { tma_store_1d(spec_g + tile * X * (M + 1), buf, (uint32_t)(rows * SPECB)); bulk_commit(); }
             } else {
                 cta_sync();
-                float2 *dst = spec_g + tile * X * (M + 1);
+                V2 *dst = spec_g + tile * X * (M + 1);
                 for (int f = t; f < rows * (M + 1); f += X) st_stream(dst + f, dense[f]);
             }
         } else {
             {   // Hermitian pre-process in registers (scale 0.5/M folded in, :1674)
-                const float sc = 0.5f / float(M);
-                const float2 a0 = drow[0], am = drow[M];      // real parts only (:1679-1684)
-                x[0] = mk<R>((a0.x + am.x) * sc, (a0.x - am.x) * sc);
+                const R sc = R(0.5) / R(M);
+                const V2 a0 = drow[0], am = drow[M];          // real parts only (:1679-1684)
+                x[0] = mk<R>(rmul(radd(a0.x, am.x), sc), rmul(rsub(a0.x, am.x), sc));
                 static_for<HALF>([&](auto K_) {
                     CIDX(k0, K_);
                     constexpr int k = k0 + 1;                 // 1 .. M/2 (k = M/2 is self-paired)
-                    const float2 a = drow[k], b = drow[M - k];
+                    const V2 a = drow[k], b = drow[M - k];
                     const twd<R> w = ld_tw(rtw + k);
-                    const float gr = a.x + b.x, gi = a.y - b.y, ur = a.x - b.x, ui = a.y + b.y;
-                    const float hr = fmaf(w.y, ui, w.x * ur), hi = fmaf(w.ny, ur, w.x * ui);
+                    const R gr = radd(a.x, b.x), gi = rsub(a.y, b.y), ur = rsub(a.x, b.x), ui = radd(a.y, b.y);
+                    const R hr = rfma(w.y, ui, rmul(w.x, ur)), hi = rfma(w.ny, ur, rmul(w.x, ui));
                     // forward form first, mirrored second: at k = M/2 the mirrored form survives (:1722-1740)
-                    x[k] = mk<R>(sc * (gr - hi), sc * (gi + hr));
-                    x[M - k] = mk<R>(sc * (gr + hi), sc * (hr - gi));
+                    x[k] = mk<R>(rmul(sc, rsub(gr, hi)), rmul(sc, radd(gi, hr)));
+                    x[M - k] = mk<R>(rmul(sc, radd(gr, hi)), rmul(sc, rsub(hr, gi)));
                 });
             }
             claim_and_issue<true>(p.ctr, pending, tiles, slot, st ^ 1, issue);
             run_pass<R, PL, 0, true>(x, tw, UTw<R, PL>::make(p, tw), 0);
             cta_sync();                                // spectrum rows and time rows alias
-            static_for<M / 2>([&](auto H_) {
-                CIDX(h, H_);
-                constexpr int s0 = slot_of_elem<PL, 0>(2 * h), s1 = slot_of_elem<PL, 0>(2 * h + 1);
-                trow[h] = make_float4(x[s0].x, x[s0].y, x[s1].x, x[s1].y);
-            });
+            if constexpr (ES == 8) {
+                double2 *tr = reinterpret_cast<double2 *>(trow);
+                static_for<M>([&](auto H_) { CIDX(h, H_); constexpr int s0 = slot_of_elem<PL, 0>(h); tr[h] = make_double2(x[s0].x, x[s0].y); });
+            } else {
+                float4 *tr = reinterpret_cast<float4 *>(trow);
+                static_for<M / 2>([&](auto H_) {
+                    CIDX(h, H_);
+                    constexpr int s0 = slot_of_elem<PL, 0>(2 * h), s1 = slot_of_elem<PL, 0>(2 * h + 1);
+                    tr[h] = make_float4(x[s0].x, x[s0].y, x[s1].x, x[s1].y);
+                });
+            }
             fence_proxy_async();
             cta_sync();
             if (t < 32) {

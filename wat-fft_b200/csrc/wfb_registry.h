@@ -127,15 +127,19 @@ template <class PL, int X, int MINB> struct TileLaunchers {
 };
 
 // persistent, fully TMA-fed thread-per-row c2c (N <= 64)
-template <class PL, int X, int MINB> struct TilePipeLaunchers {
-    static constexpr size_t smem_s = 2 * tpipe_buf_bytes<PL, X, IO_SPLIT>() + 64, smem_i = 2 * tpipe_buf_bytes<PL, X, IO_INTERLEAVED>() + 64;
+template <class PL, int X, int MINB, typename R = float> struct TilePipeLaunchers {
+    static constexpr bool F64 = sizeof(R) == 8;
+    static constexpr size_t smem_i = 2 * tpipe_buf_bytes<R, PL, X, IO_INTERLEAVED>() + 64;
+    static constexpr size_t smem_s = F64 ? 0 : 2 * tpipe_buf_bytes<float, PL, X, IO_SPLIT>() + 64;
     static constexpr size_t smem = smem_s > smem_i ? smem_s : smem_i;
     static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
         const void *k;
-        if (io == IO_SPLIT)
-            k = dir ? (const void *)k_c2c_tpipe<PL, X, IO_SPLIT, true, MINB> : (const void *)k_c2c_tpipe<PL, X, IO_SPLIT, false, MINB>;
-        else
-            k = dir ? (const void *)k_c2c_tpipe<PL, X, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_tpipe<PL, X, IO_INTERLEAVED, false, MINB>;
+        if (io == IO_SPLIT) {
+            if constexpr (F64) return cudaErrorInvalidDeviceFunction;      // the f64 modules are interleaved only
+            else k = dir ? (const void *)k_c2c_tpipe<float, PL, X, IO_SPLIT, true, MINB> : (const void *)k_c2c_tpipe<float, PL, X, IO_SPLIT, false, MINB>;
+        } else {
+            k = dir ? (const void *)k_c2c_tpipe<R, PL, X, IO_INTERLEAVED, true, MINB> : (const void *)k_c2c_tpipe<R, PL, X, IO_INTERLEAVED, false, MINB>;
+        }
         return launch_persistent(k, smem, X, (batch + X - 1) / X, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
@@ -144,13 +148,13 @@ template <class PL, int X, int MINB> struct TilePipeLaunchers {
 };
 
 // persistent, fully TMA-fed thread-per-row r2c / c2r (N = 64, 128)
-template <class PL, int X, int MINB> struct RealTilePipeLaunchers {
-    static constexpr size_t smem = 2 * rtpipe_buf_bytes<PL, X>() + 64;
+template <class PL, int X, int MINB, typename R = float> struct RealTilePipeLaunchers {
+    static constexpr size_t smem = 2 * rtpipe_buf_bytes<R, PL, X>() + 64;
     static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_persistent((const void *)k_real_tpipe<PL, X, false, MINB>, smem, X, (batch + X - 1) / X, p, s);
+        return launch_persistent((const void *)k_real_tpipe<R, PL, X, false, MINB>, smem, X, (batch + X - 1) / X, p, s);
     }
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_persistent((const void *)k_real_tpipe<PL, X, true, MINB>, smem, X, (batch + X - 1) / X, p, s);
+        return launch_persistent((const void *)k_real_tpipe<R, PL, X, true, MINB>, smem, X, (batch + X - 1) / X, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
         return Variant{name, PL::N, X, X, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
@@ -245,6 +249,7 @@ using F64_4 = Plan<4, 1, 0x4>;
 using F64_8 = Plan<8, 1, 0x222>;
 using F64_16 = Plan<16, 1, 0x44>;
 using F64_32 = Plan<32, 2, 0x2, 0x2222>;
+using T64_32 = Plan<32, 1, 0x22222>;              // thread-per-row (same radix-2 stage sequence)
 using F64_64 = Plan<64, 4, 0x4, 0x44>;
 using F64_128 = Plan<128, 8, 0x222, 0x2222>;
 using F64_256 = Plan<256, 16, 0x44, 0x44>;
