@@ -1260,7 +1260,13 @@ template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ c
 template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false, bool TS = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
-    static_assert(!C2R || X % 2 == 0, "c2r tiles need an even number of rows (16-byte alignment)");
+    static_assert(!C2R || X % 2 == 0 || X == 1, "c2r tiles: an even number of rows (16-byte alignment), or single rows");
+    // c2r with ONE row per tile (N >= 4096: a row is the 16 KB tile): rows are (M+1) bins = 8 bytes more than a multiple
+    // of 16, so the copy of row r covers (M+2) bins starting at bin -(r & 1) of the row -- 16-byte aligned start and size;
+    // the extra bin belongs to a neighbouring row and is ignored.  (The very last row of an odd batch has no bin after
+    // it: it takes the cooperative-copy path.)
+    constexpr bool SHIFT = C2R && X == 1;
+    static_assert(!SHIFT || sizeof(R) == 4, "single-row c2r tiles: f32 (f64 rows are 16-byte multiples already)");
     static_assert(!RC || (!C2R && PL::N >= 32 && PL::T * X >= 32), "row copies: r2c only (c2r rows are 8-byte aligned)");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using S = typename VecOf<R>::s;
@@ -1288,12 +1294,18 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     __syncthreads();
 
     auto tile_rows = [&](long tile) { const long row = tile * X; return (p.batch - row < X) ? (int)(p.batch - row) : X; };
-    auto tma_ok = [&](long tile) { return !C2R || (tile_rows(tile) % 2 == 0); };
+    auto tma_ok = [&](long tile) { return !C2R || (SHIFT ? ((tile & 1) || tile + 1 < p.batch) : (tile_rows(tile) % 2 == 0)); };
     auto issue = [&](long tile, int st) {
         if constexpr (TS) { bulk_wait_read_all(); __syncwarp(); }   // the stores out of this stage have drained
         if (!tma_ok(tile)) return;
         const int rows = tile_rows(tile);
-        if constexpr (!RC) {
+        if constexpr (SHIFT) {
+            if (threadIdx.x == 0) {
+                const uint32_t bytes = (uint32_t)((M + 2) * sizeof(V2));
+                mbar_expect_tx(mbar + st, bytes);
+                tma_load_1d(smem_raw + st * BUF, gin + tile * IN_ROW - (tile & 1), bytes, mbar + st);
+            }
+        } else if constexpr (!RC) {
             if (threadIdx.x == 0) {
                 const uint32_t bytes = (uint32_t)(rows * IN_ROW * sizeof(V2));
                 mbar_expect_tx(mbar + st, bytes);
@@ -1311,12 +1323,23 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     };
 
     // TS: the finished tile in stage st leaves as one bulk store (odd-sized last r2c tile: plain stores by warp 0)
+    // r2c with ONE row per tile (f32, N >= 4096): a row of (M+1) bins is 8 bytes more than a multiple of 16 and odd rows
+    // start 8 bytes off.  The row is assembled at element offset (row & 1) of the stage, M of its bins leave as one
+    // aligned bulk store (bins 0..M-1 of an even row, 1..M of an odd one) and the remaining bin as a plain store.
+    constexpr bool ROW1 = !C2R && TS && X == 1 && sizeof(R) == 4;
     auto store_tile = [&](long tile, int st) {
         if (threadIdx.x >= 32) return;
         const int count = tile_rows(tile) * OUT_ROW;
         const V2 *src = reinterpret_cast<const V2 *>(smem_raw + st * BUF);
         V2 *dst = gout + tile * X * OUT_ROW;
-        if ((count * sizeof(V2)) % 16 == 0) {
+        if constexpr (ROW1) {
+            if (threadIdx.x == 0) {
+                const int sh = (int)(tile & 1);
+                tma_store_1d(dst + sh, src + 2 * sh, (uint32_t)(M * sizeof(V2)));
+                bulk_commit();
+                st_stream(dst + (sh ? 0 : M), src[sh ? 1 : M]);
+            }
+        } else if ((count * sizeof(V2)) % 16 == 0) {
             if (threadIdx.x == 0) { tma_store_1d(dst, src, (uint32_t)(count * sizeof(V2))); bulk_commit(); }
         } else {
             for (int i = threadIdx.x; i < count; i += 32) st_stream(dst + i, src[i]);
@@ -1350,7 +1373,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
         const long row = tile * X + xi;
         const bool active = row < p.batch;
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(M);
-        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xi * RSTR;
+        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xi * RSTR + ((SHIFT && tma_ok(tile)) ? (int)(tile & 1) : 0);
 
         if constexpr (!C2R) {
             // ---------------- r2c
@@ -1359,7 +1382,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             if constexpr (TS) claim_and_issue<false>(p.ctr, pending, tiles, slot, st ^ 1, issue);   // (slot[st ^ 1] was read before the barrier)
             run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
             // TS: the result rows are dense ([X][M+1]) and alias the other groups' scratch
-            cx<R> *park = TS ? reinterpret_cast<cx<R> *>(buf) + (size_t)xi * (M + 1) : scratch;
+            cx<R> *park = TS ? reinterpret_cast<cx<R> *>(buf) + (size_t)xi * (M + 1) + (ROW1 ? (int)(tile & 1) : 0) : scratch;
             if (PL::npass() > 1) { if constexpr (TS && X > 1) __syncthreads(); else sync_transform<PL::T, X>(xi); }
             // Hermitian post-process: bin k = tid + i*T (k < M/2) pairs the thread's OWN register value Z[k] with
             // Z[M-k], which another thread of the group owns.  Only the upper half (elements >= M/2) travels

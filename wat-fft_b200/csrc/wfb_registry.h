@@ -96,17 +96,18 @@ template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ,
 };
 
 // persistent TMA-pipelined r2c / c2r (scalar lanes)
-template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false> struct RealPipeLaunchers {
+// XI: rows per tile of the c2r direction (1 = single-row tiles with shifted bulk copies, see k_real_pipe)
+template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false, int XI = X> struct RealPipeLaunchers {
     static constexpr size_t smem_f = 2 * real_pipe_buf_bytes<R, PL, PQ, X, false>() + 64;
-    static constexpr size_t smem_i = 2 * real_pipe_buf_bytes<R, PL, PQ, X, true>() + 64;
+    static constexpr size_t smem_i = 2 * real_pipe_buf_bytes<R, PL, PQ, XI, true>() + 64;
     static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
         return launch_persistent((const void *)k_real_pipe<R, PL, X, PQ, false, MINB, RC, TS>, smem_f, PL::T * X, (batch + X - 1) / X, p, s);
     }
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_persistent((const void *)k_real_pipe<R, PL, X, PQ, true, MINB, false, TS>, smem_i, PL::T * X, (batch + X - 1) / X, p, s);
+        return launch_persistent((const void *)k_real_pipe<R, PL, XI, PQ, true, MINB, false, TS>, smem_i, PL::T * XI, (batch + XI - 1) / XI, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem_i, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
+        return Variant{name, PL::N, PL::T * X, X, smem_i > smem_f ? smem_i : smem_f, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};
     }
 };
 

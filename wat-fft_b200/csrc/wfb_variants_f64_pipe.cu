@@ -11,6 +11,7 @@ const std::vector<Variant> &variants_f64_pipe() {
     static const std::vector<Variant> v = {
         VP(F64_256, 8, 2, 5), VP(F64_512, 4, 2, 30), VP(F64_1024, 2, 2, 30), VP(F64_2048, 1, 2, 30), VP(F64_4096, 1, 1, 30),
         // results leave as bulk stores out of the stage buffer (see k_c2c_pipe / k_real_pipe, TS): defaults from N = 256
+        VTS(F64_64, 16, 2, 60), VTS(F64_128, 8, 2, 60), VRTS(F64_64, 16, 2, 60),
         VTS(F64_256, 8, 2, 60), VTS(F64_512, 4, 2, 60), VTS(F64_1024, 2, 2, 60), VTS(F64_2048, 1, 2, 60), VTS(F64_4096, 1, 1, 60),
         VRTS(F64_128, 16, 2, 60), VRTS(F64_256, 8, 2, 60), VRTS(F64_512, 4, 2, 60), VRTS(F64_1024, 2, 2, 60), VRTS(F64_2048, 2, 1, 60),
         VR(F64_128, 16, 2, 30), VR(F64_256, 8, 2, 30), VR(F64_512, 4, 2, 5, 30), VR(F64_1024, 2, 2, 30), VR(F64_2048, 2, 1, 5),
