@@ -56,7 +56,7 @@ def launches():
             other[0] += us; other[1] += 1
     total = sum(v[0] for v in per.values())
     out = [f"# Round {RND[1:].lstrip('0')} — ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`", "",
-           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv`; listed: torch's input generation, the warm-up and the",
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv`; listed: torch's input generation, the warm-up and the",
            "timed steps (the capture continues into the staged end-to-end phase, whose per-chunk launches are left out here).",
            "Per-launch times are cold-cache and serialised under the profiler, so compare SHARES, not absolutes.",
            f"Raw CSV: `profiles/{RND}_launches.csv`.  The same command ran to exit 0 without ncu first.", "",
