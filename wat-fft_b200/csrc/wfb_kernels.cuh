@@ -1279,6 +1279,13 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     constexpr size_t BUF = real_pipe_buf_bytes<R, PL, PADQ, X, C2R>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
+    // r2c with bulk stores and thread groups narrower than a shared-memory phase (T < 16 lanes of 8 bytes, < 8 of 16):
+    // the GP = phase/T groups that share a phase take rows T apart -- the dense result rows have an odd stride
+    // ((M+1) bins), so rows h, h+T, ... land in disjoint bank ranges, while adjacent rows would overlap in all but one
+    // bank (ncu: 2-way conflicts on every park/result access at N = 256).  Row of the tile this group works on:
+    constexpr int PHL = 128 / (int)sizeof(typename VecOf<R>::v2);     // lanes per phase
+    constexpr bool ROWMAP = !C2R && TS && PL::T < PHL && X % PHL == 0;
+    const int xr = ROWMAP ? ((xi / (PHL / PL::T)) / PL::T) * PHL + (xi / (PHL / PL::T)) % PL::T + PL::T * (xi % (PHL / PL::T)) : xi;
     const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
     const typename RT<R>::twel *rtw = reinterpret_cast<const typename RT<R>::twel *>(p.rtw);
     const long tiles = (p.batch + X - 1) / X;
@@ -1370,10 +1377,10 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             for (int i = threadIdx.x; i < count; i += PL::T * X) dst[i] = ld_stream(gin + tile * X * IN_ROW + i);
             __syncthreads();
         }
-        const long row = tile * X + xi;
+        const long row = tile * X + xr;
         const bool active = row < p.batch;
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(M);
-        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xi * RSTR + ((SHIFT && tma_ok(tile)) ? (int)(tile & 1) : 0);
+        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xr * RSTR + ((SHIFT && tma_ok(tile)) ? (int)(tile & 1) : 0);
 
         if constexpr (!C2R) {
             // ---------------- r2c
@@ -1382,7 +1389,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             if constexpr (TS) claim_and_issue<false>(p.ctr, pending, tiles, slot, st ^ 1, issue);   // (slot[st ^ 1] was read before the barrier)
             run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
             // TS: the result rows are dense ([X][M+1]) and alias the other groups' scratch
-            cx<R> *park = TS ? reinterpret_cast<cx<R> *>(buf) + (size_t)xi * (M + 1) + (ROW1 ? (int)(tile & 1) : 0) : scratch;
+            cx<R> *park = TS ? reinterpret_cast<cx<R> *>(buf) + (size_t)xr * (M + 1) + (ROW1 ? (int)(tile & 1) : 0) : scratch;
             if (PL::npass() > 1) { if constexpr (TS && X > 1) __syncthreads(); else sync_transform<PL::T, X>(xi); }
             // Hermitian post-process: bin k = tid + i*T (k < M/2) pairs the thread's OWN register value Z[k] with
             // Z[M-k], which another thread of the group owns.  Only the upper half (elements >= M/2) travels
