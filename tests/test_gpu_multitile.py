@@ -12,6 +12,8 @@ from conftest import f32_bound, f64_bound, rel_err
 
 pytestmark = pytest.mark.gpu
 
+REPEATS = 6          # identical launches must give identical bits: a refill/drain race would not
+
 TARGET_BYTES = 96 << 20        # of input per case: >= 3 tiles of 16-32 KB for each of the <= 1776 resident CTAs
 SAMPLES = 96
 
@@ -41,6 +43,12 @@ def test_c2c_f32_many_tiles(wf, oracle, n, layout):
         plan = wf.Plan(C.C2C, C.F32, C.SPLIT, n, batch, 0, flags)
         plan.exec_device(C.FORWARD, (re.data_ptr(), im.data_ptr()), (ore.data_ptr(), oim.data_ptr()))
         plan.sync()
+        o2r, o2i = torch.empty_like(re), torch.empty_like(im)
+        for _ in range(REPEATS):
+            plan.exec_device(C.FORWARD, (re.data_ptr(), im.data_ptr()), (o2r.data_ptr(), o2i.data_ptr()))
+            plan.sync()
+            assert torch.equal(o2r, ore) and torch.equal(o2i, oim), (n, "forward launches differ bitwise")
+        del o2r, o2i
         for r in _rows(batch, n):
             a, b = re[r * n:(r + 1) * n].cpu().numpy(), im[r * n:(r + 1) * n].cpu().numpy()
             er, ei = oracle.fft_split_f32(a, b)
@@ -78,6 +86,13 @@ def test_real_f32_many_tiles(wf, oracle, n):
     plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
     plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))
     plan.sync()
+    s2, b2 = torch.empty_like(spec), torch.empty_like(back)
+    for _ in range(REPEATS):
+        plan.exec_device(C.FORWARD, (x.data_ptr(), None), (s2.data_ptr(), None))
+        plan.exec_device(C.INVERSE, (s2.data_ptr(), None), (b2.data_ptr(), None))
+        plan.sync()
+        assert torch.equal(s2, spec) and torch.equal(b2, back), (n, "launches differ bitwise")
+    del s2, b2
     for r in _rows(batch, n):
         a = x[r * n:(r + 1) * n].cpu().numpy()
         s = spec[r * (n + 2):(r + 1) * (n + 2)].cpu().numpy()
@@ -99,6 +114,12 @@ def test_c2c_f64_many_tiles(wf, oracle, n):
     plan = wf.Plan(C.C2C, C.F64, C.INTERLEAVED, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
     plan.exec_device(C.FORWARD, (z.data_ptr(), None), (o.data_ptr(), None))
     plan.sync()
+    o2 = torch.empty_like(o)
+    for _ in range(REPEATS):
+        plan.exec_device(C.FORWARD, (z.data_ptr(), None), (o2.data_ptr(), None))
+        plan.sync()
+        assert torch.equal(o2, o), (n, "forward launches differ bitwise")
+    del o2
     for r in _rows(batch, n)[::3]:
         a = z[r * 2 * n:(r + 1) * 2 * n].cpu().numpy()
         assert rel_err(o[r * 2 * n:(r + 1) * 2 * n].cpu().numpy(), oracle.fft_f64(a), a) <= f64_bound(n), (n, r)
@@ -122,6 +143,13 @@ def test_real_f64_many_tiles(wf, oracle, n):
     plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
     plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))      # f64 c2r: extension, round trip only
     plan.sync()
+    s2, b2 = torch.empty_like(spec), torch.empty_like(back)
+    for _ in range(REPEATS):
+        plan.exec_device(C.FORWARD, (x.data_ptr(), None), (s2.data_ptr(), None))
+        plan.exec_device(C.INVERSE, (s2.data_ptr(), None), (b2.data_ptr(), None))
+        plan.sync()
+        assert torch.equal(s2, spec) and torch.equal(b2, back), (n, "launches differ bitwise")
+    del s2, b2
     for r in _rows(batch, n)[::3]:
         a = x[r * n:(r + 1) * n].cpu().numpy()
         assert rel_err(spec[r * (n + 2):(r + 1) * (n + 2)].cpu().numpy(), oracle.rfft_f64(a), a) <= f64_bound(n), (n, r)
