@@ -86,10 +86,10 @@ cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long c
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// Per-launch tile counters of the persistent kernels: a ring of zero-initialised 64-bit slots per device.
-// A slot is re-zeroed on the launching stream right before the kernel that uses it; it would only be
-// reused while still live if 4096 persistent launches were outstanding across DIFFERENT streams.
-static cudaError_t next_counter(cudaStream_t s, unsigned long long **out) {
+// Per-launch tile counters of the persistent kernels: a ring of {claims, departures} pairs per device, zeroed once
+// when the ring is created.  Every kernel leaves its pair at zero again (claim_epilogue), so nothing has to be cleared
+// between launches; a pair would only be reused while still live if 4096 persistent launches were outstanding at once.
+static cudaError_t next_counter(cudaStream_t, unsigned long long **out) {
     enum { RING = 4096 };
     static std::map<int, unsigned long long *> rings;
     static std::map<int, unsigned> heads;
@@ -102,16 +102,19 @@ static cudaError_t next_counter(cudaStream_t s, unsigned long long **out) {
         auto it = rings.find(dev);
         if (it == rings.end()) {
             unsigned long long *r = nullptr;
-            cudaError_t e = cudaMalloc(&r, RING * sizeof(unsigned long long));
+            cudaError_t e = cudaMalloc(&r, 2 * RING * sizeof(unsigned long long));
             if (e != cudaSuccess) return e;
+            // plan streams are non-blocking (they do not order against the legacy stream): finish the clear here
+            if ((e = cudaMemset(r, 0, 2 * RING * sizeof(unsigned long long))) != cudaSuccess) return e;
+            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
             it = rings.emplace(dev, r).first;
             heads[dev] = 0;
         }
         ring = it->second;
         idx = heads[dev]++ % RING;
     }
-    *out = ring + idx;
-    return cudaMemsetAsync(*out, 0, sizeof(unsigned long long), s);
+    *out = ring + 2 * idx;
+    return cudaSuccess;
 }
 
 cudaError_t launch_persistent_raw(const void *kernel, size_t smem, int threads, long work_items, void *params, cudaStream_t s) {

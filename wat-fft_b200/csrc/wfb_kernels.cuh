@@ -400,7 +400,7 @@ struct KParams {
     const void *rtw;           // W_Nreal^k, k = 0..M, for the real transforms
     long batch;
     double scale;              // applied on store (1/N for the inverse c2c)
-    unsigned long long *ctr;   // persistent kernels: zeroed tile counter of this launch (dynamic tile claims)
+    unsigned long long *ctr;   // persistent kernels: this launch's counter pair {tile claims, departed CTAs}, zero on entry AND on exit
     // the first TW0_BYTES of the stage table `tw` (scalar-lane variants): pass 0's thread-independent twiddles,
     // read as constant-bank operands (see CTw)
     enum { TW0_BYTES = 1008 };                         // 63 entries of a radix-64 opening pass in f64
@@ -875,6 +875,22 @@ __device__ __forceinline__ void claim_and_issue(unsigned long long *ctr, long &p
     }
 }
 
+// Epilogue of every persistent kernel: the last CTA to leave puts the launch's counter pair {claims, departures} back to
+// zero, so the host never has to clear a slot between launches (a cudaMemsetAsync in front of every kernel cost one more
+// stream-order dependency per launch).  Each CTA's claims have returned before it reports its departure; the fences order
+// them against the reset by the CTA that sees gridDim.x - 1 earlier departures.
+__device__ __forceinline__ void claim_epilogue(unsigned long long *ctr) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long gone = atomicAdd(ctr + 1, 1ULL);
+        if (gone == gridDim.x - 1) {
+            __threadfence();
+            ctr[0] = 0ULL;
+            ctr[1] = 0ULL;
+        }
+    }
+}
+
 template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr size_t pipe_buf_bytes() {
     size_t a = sizeof(cx<R>) * (size_t)padded_size<PADQ>(PL::N) * X;
     return (a + 127) / 128 * 128;
@@ -1076,6 +1092,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         }
     }
     if constexpr (TS) { if (threadIdx.x < 32) bulk_wait_read_all(); }   // shared memory must outlive the stores that read it
+    claim_epilogue(p.ctr);
 }
 
 
@@ -1235,6 +1252,7 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
         }
     }
     if (t < 32) bulk_wait_read_all();                  // shared memory must outlive the stores that read it
+    claim_epilogue(p.ctr);
 }
 
 
@@ -1483,6 +1501,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
         }
     }
     if constexpr (TS) { if (threadIdx.x < 32) bulk_wait_read_all(); }   // shared memory must outlive the stores that read it
+    claim_epilogue(p.ctr);
 }
 
 
@@ -1821,6 +1840,7 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
         }
     }
     if (t < 32) bulk_wait_read_all();                  // shared memory must outlive the stores that read it
+    claim_epilogue(p.ctr);
 }
 
 
@@ -2042,6 +2062,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(const __grid_const
         sync_transform<PL::T, X>(xi);
         if (active) stft_post<PL, LAST, KM>(x, scratch, rtw, tid, frame, sp);
     }
+    claim_epilogue(sp.ctr);
 }
 
 }  // namespace wfb
