@@ -1278,13 +1278,12 @@ template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ c
 template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false, bool TS = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
-    static_assert(!C2R || X % 2 == 0 || X == 1, "c2r tiles: an even number of rows (16-byte alignment), or single rows");
+    static_assert(!C2R || X % 2 == 0 || X == 1 || sizeof(R) == 8, "f32 c2r tiles: an even number of rows (16-byte alignment), or single rows");
     // c2r with ONE row per tile (N >= 4096: a row is the 16 KB tile): rows are (M+1) bins = 8 bytes more than a multiple
     // of 16, so the copy of row r covers (M+2) bins starting at bin -(r & 1) of the row -- 16-byte aligned start and size;
     // the extra bin belongs to a neighbouring row and is ignored.  (The very last row of an odd batch has no bin after
     // it: it takes the cooperative-copy path.)
-    constexpr bool SHIFT = C2R && X == 1;
-    static_assert(!SHIFT || sizeof(R) == 4, "single-row c2r tiles: f32 (f64 rows are 16-byte multiples already)");
+    constexpr bool SHIFT = C2R && X == 1 && sizeof(R) == 4;     // (f64 rows are 16-byte multiples already)
     static_assert(!RC || (!C2R && PL::N >= 32 && PL::T * X >= 32), "row copies: r2c only (c2r rows are 8-byte aligned)");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using S = typename VecOf<R>::s;
@@ -1319,7 +1318,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     __syncthreads();
 
     auto tile_rows = [&](long tile) { const long row = tile * X; return (p.batch - row < X) ? (int)(p.batch - row) : X; };
-    auto tma_ok = [&](long tile) { return !C2R || (SHIFT ? ((tile & 1) || tile + 1 < p.batch) : (tile_rows(tile) % 2 == 0)); };
+    auto tma_ok = [&](long tile) { return !C2R || sizeof(R) == 8 || (SHIFT ? ((tile & 1) || tile + 1 < p.batch) : (tile_rows(tile) % 2 == 0)); };
     auto issue = [&](long tile, int st) {
         if constexpr (TS) { bulk_wait_read_all(); __syncwarp(); }   // the stores out of this stage have drained
         if (!tma_ok(tile)) return;

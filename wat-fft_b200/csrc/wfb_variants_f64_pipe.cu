@@ -14,6 +14,9 @@ const std::vector<Variant> &variants_f64_pipe() {
         VTS(F64_64, 16, 2, 60), VTS(F64_128, 8, 2, 60), VRTS(F64_64, 16, 2, 60),
         VTS(F64_256, 8, 2, 60), VTS(F64_512, 4, 2, 60), VTS(F64_1024, 2, 2, 60), VTS(F64_2048, 1, 2, 60), VTS(F64_4096, 1, 1, 60),
         VRTS(F64_128, 16, 2, 60), VRTS(F64_256, 8, 2, 60), VRTS(F64_512, 4, 2, 60), VRTS(F64_1024, 2, 2, 60), VRTS(F64_2048, 2, 1, 60),
+        // 16 KB tiles (f64 rows are twice as wide): +1..8 % at N >= 1024; single f64 rows are 16-byte multiples, no shift needed
+        VTS(F64_512, 2, 2, 61), VTS(F64_1024, 1, 2, 61),
+        VRTS(F64_512, 2, 2, 61), VRTS(F64_1024, 1, 2, 61), VRTS(F64_2048, 1, 1, 61),
         VR(F64_128, 16, 2, 30), VR(F64_256, 8, 2, 30), VR(F64_512, 4, 2, 5, 30), VR(F64_1024, 2, 2, 30), VR(F64_2048, 2, 1, 5),
     };
     return v;
