@@ -256,6 +256,7 @@ using F64_128 = Plan<128, 8, 0x222, 0x2222>;
 using F64_256 = Plan<256, 16, 0x44, 0x44>;
 using F64_512 = Plan<512, 32, 0x2, 0x2222, 0x2222>;
 using F64_1024 = Plan<1024, 64, 0x4, 0x44, 0x44>;
+using D32_512 = Plan<512, 16, 0x22222, 0x2222>;      // 32 values per thread: the same nine radix-2 stages, one exchange
 using F64_2048 = Plan<2048, 128, 0x222, 0x2222, 0x2222>;
 using F64_4096 = Plan<4096, 256, 0x44, 0x44, 0x44>;
 using F64_8192 = Plan<8192, 512, 0x2, 0x2222, 0x2222, 0x2222>;
