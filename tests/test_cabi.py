@@ -115,3 +115,26 @@ def test_product_does_not_import_oracle():
             text = p.read_text(errors="ignore")
             assert "libwatfft_oracle" not in text and "watfft_oracle.c" not in text and "libwatref" not in text, p
             assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), p
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (what cgo / N-API / ctypes-style binders consume),
+    and a C translation unit must link against the library's exported symbols."""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    src = tmp_path / "use_header.c"
+    src.write_text(
+        '#include "watfft_b200.h"\n'
+        "int main(void) {\n"
+        "    int lo = 0, hi = 0;\n"
+        "    if (wfb_size_range(WFB_C2C, WFB_F32, WFB_SPLIT, &lo, &hi) != WFB_OK) return 1;\n"
+        "    return (lo == 4 && hi == 8192 && wfb_strerror(WFB_ERR_NO_DEVICE)[0]) ? 0 : 2;\n"
+        "}\n")
+    exe = tmp_path / "use_header"
+    lib_dir = root / "wat-fft_b200"
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", str(root / "include"), str(src), "-o", str(exe),
+                        "-L", str(lib_dir), "-lwatfft_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)       # pure host logic: runs without a GPU
+    assert r.returncode == 0, (r.returncode, r.stderr)
+
