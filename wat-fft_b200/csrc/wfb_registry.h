@@ -242,6 +242,7 @@ using P64_1024 = Plan<1024, 16, 0x44, 0x444>;
 // f32 only (tolerance-based parity lets the stage radices be regrouped as 2,4,4 | 2,4,4).
 using P32_1024 = Plan<1024, 32, 0x244, 0x244>;    // pad slot per 32 values
 using P32_512 = Plan<512, 16, 0x244, 0x44>;
+using P32_8192 = Plan<8192, 256, 0x244, 0x44, 0x44>;   // the same seven stages as F32_8192 in three passes instead of four
 // thread-per-row plans for the tile kernels (whole transform in registers)
 using T32_32 = Plan<32, 1, 0x244>;
 using T32_64 = Plan<64, 1, 0x444>;

@@ -24,6 +24,8 @@ const std::vector<Variant> &variants_f32_pipe() {
         // (profiles/: +1..4 % at burst clocks, +3..8 % power-capped; N = 4096: 86 -> 92 % at burst, equal power-capped)
         VTS(F32_128, 16, 2, true, 16, 60), VTS(F32_256, 8, 2, false, 16, 60), VTS(P32_512, 4, 2, false, 16, 60), VTS(P32_1024, 2, 2, false, 32, 60),
         VTS(F32_2048, 1, 4, false, 16, 60), VTS(P64_4096, 1, 1, false, 64, 20), VTS(F32_4096, 1, 2, false, 16, 60), VTS(F32_8192, 1, 1, false, 16, 60),
+        // N = 8192: three passes (32 values per thread) instead of four: 69 -> 82 %
+        VTS(P32_8192, 1, 1, false, 16, 61),
         VP64(P64_4096, 1, 1, 31),   // one exchange: 3 % slower than F32_4096_pipe1 at burst clocks, 4 % faster power-capped
          VP64(P64_2048, 1, 1, 20), VP64(P64_1024, 2, 1, 20),
     };

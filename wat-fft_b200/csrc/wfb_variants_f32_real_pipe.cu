@@ -21,6 +21,7 @@ const std::vector<Variant> &variants_f32_real_pipe() {
         // (a row IS the 16 KB tile there; rows are 8 bytes off a 16-byte multiple, see SHIFT / ROW1 in k_real_pipe.
         //  N = 4096: r2c 95 -> 97 %, c2r 87 -> 97 % of the HBM peak at burst clocks; N = 8192: 79 -> 88-89 %)
         RealPipeLaunchers<float, F32_2048, 1, 2, false, 16, true, 1>::make("F32_2048_rpipe1_ts", 61), RealPipeLaunchers<float, F32_4096, 1, 1, false, 16, true, 1>::make("F32_4096_rpipe1_ts", 61),
+        RealPipeLaunchers<float, P32_8192, 1, 1, false, 16, true, 1>::make("P32_8192_rpipe1_ts", 61),
         VR(F32_1024, 2, 2, 30), VR(F32_2048, 2, 2, 30, 9), VR(F32_4096, 2, 1, 30),
     };
     return v;
