@@ -111,6 +111,27 @@ PLANS_F64 = {
     4096: (256, [0x44, 0x44, 0x44]), 8192: (512, [0x2, 0x2222, 0x2222, 0x2222]),
 }
 
+# the wider plans of csrc/wfb_registry.h: (N, T, pass codes, pad quantum, words per element)
+EXTRA_PLANS = {
+    "P32_512": (512, 16, [0x244, 0x44], 16, 2), "P32_1024": (1024, 32, [0x244, 0x244], 32, 2),
+    "P32_8192": (8192, 256, [0x244, 0x44, 0x44], 16, 2),
+    "P64_4096": (4096, 64, [0x444, 0x444], 64, 2), "P64_2048": (2048, 32, [0x244, 0x444], 64, 2),
+    "P64_1024": (1024, 16, [0x44, 0x444], 64, 2),
+    "D32_512": (512, 16, [0x22222, 0x2222], 16, 4),
+}
+
+
+def registered_plans():
+    """every multi-pass plan with the pad quantum its kernels are instantiated with"""
+    out = {}
+    for n, (t, codes) in PLANS_F32.items():
+        out[f"F32_{n}"] = (n, t, codes, 16, 2)
+    for n, (t, codes) in PLANS_F64.items():
+        out[f"F64_{n}"] = (n, t, codes, 16, 4)
+    out.update(EXTRA_PLANS)
+    return out
+
+
 if __name__ == "__main__":
     for name, plans, ew in (("f32", PLANS_F32, 2), ("f64", PLANS_F64, 4)):
         for padq in (0, 4, 8, 16, 32):
