@@ -120,7 +120,9 @@ WFB_API int wfb_sync(wfb_plan *plan);
 WFB_API void *wfb_plan_stream(wfb_plan *plan);
 
 /* ---- introspection / tuning ------------------------------------------- */
-/* Kernel variants compiled for this plan's (kind, precision, n); variant 0 is the default. */
+/* Kernel variants compiled for this plan's (kind, precision, n); variant 0 is the default.
+ * wfb_plan_set_variant pins BOTH directions to that kernel and switches the zero-copy small-batch path off for the
+ * plan (WFB_OPT_MAPPED_MAX_BYTES = 0), so that wfb_exec runs exactly the kernel that was asked for. */
 WFB_API int wfb_plan_variant_count(wfb_plan *plan);
 WFB_API int wfb_plan_set_variant(wfb_plan *plan, int variant);
 WFB_API const char *wfb_plan_variant_name(wfb_plan *plan, int variant);
@@ -128,6 +130,24 @@ WFB_API const char *wfb_plan_variant_name(wfb_plan *plan, int variant);
 WFB_API int wfb_plan_current_variant(wfb_plan *plan, int direction);
 /* Algorithmic bytes one exec moves (one read + one write of the payload; twiddles excluded). */
 WFB_API size_t wfb_plan_algorithmic_bytes(wfb_plan *plan);
+
+/* Staging knobs of wfb_exec (defaults from the environment: WFB_MAPPED_MAX_KB, WFB_STAGE_CHUNK_MB, WFB_STAGE_STREAMS).
+ *   WFB_OPT_MAPPED_MAX_BYTES   payloads (input + output bytes) up to this size skip the copies: ONE kernel launch reads
+ *                              and writes the pinned, device-mapped host buffers directly.  This is the path of the
+ *                              reference's own call shape, batch = 1 (index.js:84-89).  0 disables it.
+ *   WFB_OPT_STAGE_CHUNK_BYTES  bytes of the widest plane per chunk of the H2D / kernel / D2H pipeline
+ *   WFB_OPT_STAGE_STREAMS      streams the chunks cycle over (1..6) */
+enum { WFB_OPT_MAPPED_MAX_BYTES = 0, WFB_OPT_STAGE_CHUNK_BYTES = 1, WFB_OPT_STAGE_STREAMS = 2 };
+WFB_API int wfb_plan_set_option(wfb_plan *plan, int option, long value);
+WFB_API long wfb_plan_get_option(wfb_plan *plan, int option);
+/* Which path the latest wfb_exec took. */
+enum { WFB_PATH_NONE = 0, WFB_PATH_STAGED = 1, WFB_PATH_PIPELINED = 2, WFB_PATH_MAPPED = 3 };
+WFB_API int wfb_plan_last_path(wfb_plan *plan);
+
+/* Pinned-copy ceiling of the host link of `device`: gbs[0] = H2D alone, gbs[1] = D2H alone, gbs[2], gbs[3] = H2D and
+ * D2H running at the same time (GB/s each; `bytes` per copy, `iters` copies per direction).  The denominator of the
+ * end-to-end (host-buffer) throughput: wfb_exec cannot move a transform faster than its bytes cross this link. */
+WFB_API int wfb_pcie_probe(int device, size_t bytes, int iters, double gbs[4]);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 WFB_API unsigned long long wfb_kernel_launch_count(void);
 

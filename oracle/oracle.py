@@ -264,6 +264,66 @@ class WatRef:
                  o0[0], o0[1], o0[2], src0, o1[0], o1[1], o1[2], src1, in0.shape[0], reps, threads)
 
 
+class WatRefPool:
+    """Persistent pthread pool over the transpiled reference modules (oracle/watref_threads.c): one private module
+    memory per worker, `prepare()` = instantiate + precompute once per size (untimed, like
+    benchmarks/lib/wat-contexts.js:110-131), `run()` = the timed memcpy-in + transform loop over the rows."""
+
+    def __init__(self, ref: "WatRef", threads=None):
+        self.ref, self.lib = ref, ref.lib
+        vp, sz, u32, lg, dbl = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_long, ctypes.c_double
+        L = self.lib
+        L.watref_pool_create.restype, L.watref_pool_create.argtypes = vp, [ctypes.c_int]
+        L.watref_pool_destroy.restype, L.watref_pool_destroy.argtypes = None, [vp]
+        L.watref_pool_prepare.restype, L.watref_pool_prepare.argtypes = None, [vp, vp, u32, u32]
+        L.watref_pool_run.restype = dbl
+        L.watref_pool_run.argtypes = [vp, vp, u32, vp, sz, sz, u32, vp, sz, sz, u32, vp, sz, sz, u32, vp, sz, sz, u32, lg, lg]
+        L.watref_pool_run_stft.restype = dbl
+        L.watref_pool_run_stft.argtypes = [vp, vp, u32, vp, vp, ctypes.c_int, ctypes.c_int, lg, dbl, dbl, vp, lg]
+        self.threads = threads or os.cpu_count() or 1
+        self._p = L.watref_pool_create(self.threads)
+
+    def _fn(self, module, export):
+        return ctypes.cast(getattr(self.lib, f"watref_{module}_{export}"), ctypes.c_void_p)
+
+    def prepare(self, module, precompute, n):
+        pages = getattr(self.lib, f"watref_{module}_pages")
+        pages.restype = ctypes.c_uint32
+        self.lib.watref_pool_prepare(self._p, self._fn(module, precompute), pages(), n)
+
+    def run(self, module, export, n, in0, dst0=0, in1=None, dst1=0, out0=None, src0=0, out1=None, src1=0, reps=1):
+        """rows of in0 (2-D, C-contiguous) -> memory offset dst0, then export(n); optional copy-out.  Wall seconds."""
+        def plane(a):
+            if a is None:
+                return None, 0, 0
+            assert a.ndim == 2 and a.flags.c_contiguous
+            return a.ctypes.data, a.shape[1] * a.itemsize, a.strides[0]
+        i0, i1, o0, o1 = plane(in0), plane(in1), plane(out0), plane(out1)
+        return self.lib.watref_pool_run(self._p, self._fn(module, export), n, i0[0], i0[1], i0[2], dst0, i1[0], i1[1], i1[2], dst1,
+                                        o0[0], o0[1], o0[2], src0, o1[0], o1[1], o1[2], src1, in0.shape[0], reps)
+
+    def run_stft(self, samples, fft_size, hop, window, gain, range_db, out, reps=1):
+        """generateSpectrogram's per-frame loop (C port) around the module's rfft_split; prepare() must have been
+        called with precompute_rfft_twiddles_split(fft_size).  Wall seconds."""
+        assert samples.dtype == np.float32 and window.dtype == np.float64 and out.dtype == np.float32
+        frames = (len(samples) - len(window)) // hop + 1
+        assert out.size >= frames * (fft_size // 2 + 1)
+        return self.lib.watref_pool_run_stft(self._p, self._fn("fft_split_native_f32", "rfft_split"), fft_size,
+                                             samples.ctypes.data, window.ctypes.data, len(window), hop, frames,
+                                             float(gain), float(range_db), out.ctypes.data, reps)
+
+    def close(self):
+        if self._p:
+            self.lib.watref_pool_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ----------------------------------------------------------------------
 # Reference fixtures restated
 # ----------------------------------------------------------------------

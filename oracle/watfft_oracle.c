@@ -6,12 +6,12 @@
  * bench.py's cpu_baseline / --impl reference legs use it, and only as the
  * checker or the reported CPU baseline.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_watref.py compares every entry
+ * Parity status: PINNED.  tests/test_oracle_pinning.py compares every entry
  * point below against oracle/_ref/libwatref.so (the reference's own WAT
- * modules transpiled to C by oracle/wat2c.py and compiled without FMA), and
- * tests/test_oracle_golden.py checks the reference's inline golden vectors
- * (tests/golden_reference.test.js:32-214) and the fixtures committed under
- * tests/golden/ (generated from libwatref by tests/golden/make_fixtures.py).
+ * modules transpiled to C by oracle/wat2c.py and compiled without FMA) and
+ * against the fixtures committed under tests/golden/ (generated from libwatref
+ * by tests/golden/make_fixtures.py); tests/test_reference_suites.py checks the
+ * reference's inline golden vectors (tests/golden_reference.test.js:32-214).
  *
  * All citations are file:line under the reference repo (EmNudge/wat-fft).
  * Build with -ffp-contract=off: WebAssembly has no fused multiply-add.

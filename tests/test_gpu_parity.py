@@ -9,6 +9,15 @@ from conftest import f32_bound, f64_bound, rel_err
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["copy", "zero-copy"])
+def staging_path(request, monkeypatch):
+    """Every case runs through BOTH host-buffer paths of wfb_exec: the staged copies around the plan's default (TMA)
+    kernel, and the zero-copy path (one direct-load kernel on the mapped host buffers) that small payloads take by
+    default.  The plan reads the threshold from the environment when it is created."""
+    monkeypatch.setenv("WFB_MAPPED_MAX_KB", "0" if request.param == "copy" else "16384")
+    return request.param
+
 C2C_SIZES = [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
 R2C_F32_SIZES = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
 R2C_F64_SIZES = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]

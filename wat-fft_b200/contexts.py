@@ -80,6 +80,16 @@ class Plan:
     def algorithmic_bytes(self):
         return self._lib.wfb_plan_algorithmic_bytes(self._p)
 
+    def set_option(self, option, value):
+        C.check(self._lib.wfb_plan_set_option(self._p, option, int(value)))
+
+    def get_option(self, option):
+        return self._lib.wfb_plan_get_option(self._p, option)
+
+    def last_path(self):
+        """C.PATH_*: how the latest exec() moved its data (staged copies, chunked pipeline, or zero-copy)."""
+        return self._lib.wfb_plan_last_path(self._p)
+
     def destroy(self):
         if getattr(self, "_p", None):
             self._lib.wfb_plan_destroy(self._p)
@@ -199,7 +209,8 @@ def createRFFT(size, batch=1, device=0):
 
 
 def createRFFTf32(size, batch=1, device=0):
-    """f32 real FFT with the rfft_split contract (index.js:156-178; N >= 32)."""
+    """f32 real FFT with the rfft_split contract (index.js:156-178).  N >= 8: sizes 8 and 16 follow the
+    public createRFFTf32 context (fft_real_f32_dual, benchmarks/shared/wat-surfaces.mjs:133-141)."""
     return _RealContext(size, C.F32, batch, device)
 
 

@@ -164,20 +164,29 @@ struct wfb_plan {
     std::vector<const Variant *> variants;
     int variant;                       // forward-direction kernel variant
     int variant_inv;                   // inverse-direction kernel variant
-    void *d_tw_fwd[8], *d_tw_inv[8];   // per variant
+    void *d_tw_fwd[8], *d_tw_inv[8];   // per variant; built and uploaded on the variant's first launch (ensure_tables)
     void *d_rtw[8];                    // per variant (table format depends on the lane type)
+    void *d_tables[8];                 // the one allocation d_tw_fwd / d_tw_inv / d_rtw of a variant point into
+    bool tables_ready[8];
     std::vector<unsigned char> h_tw0_fwd[8], h_tw0_inv[8];   // head of each table for KParams::tw0 (scalar-lane variants)
     // buffers: C2C -> plane 0 / plane 1; R2C -> time / spectrum
     void *d_buf[2];
     void *h_buf[2];
     size_t bytes[2];
     bool host_alias;                   // R2C batch == 1: both host views share one allocation
+    void *hd_buf[2];                   // device-side addresses of the (mapped) host buffers: the zero-copy path
+    int mapped_variant;                // direct-load kernel the zero-copy path launches
+    long mapped_max_bytes;             // zero-copy below this many payload bytes (in + out)
+    long stage_chunk_bytes;            // staging pipeline: bytes of the widest plane per chunk
+    int stage_streams;                 // ... and the number of streams the chunks cycle over
+    int last_path;                     // WFB_PATH_* of the latest wfb_exec
     cudaStream_t stream;
     // staging pipeline: chunks of rows cycle over these streams so the H2D copy of chunk c+1, the
     // kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex)
     enum { NPIPE = 6 };
     cudaStream_t pipe[NPIPE];
     cudaEvent_t pipe_done[NPIPE], start_ev;
+    bool pipe_ready;                   // streams / events above exist (created by the first pipelined exec)
 };
 
 static int check_device(int device) {
@@ -297,35 +306,79 @@ static int upload_tables(wfb_plan *pl, int vi) {
         head(fwd, pl->h_tw0_fwd[vi]); head(inv, pl->h_tw0_inv[vi]);
     }
     widen(fwd); widen(inv);
-    CK(cudaMalloc(&pl->d_tw_fwd[vi], fwd.size() * sizeof(R)));
-    CK(cudaMalloc(&pl->d_tw_inv[vi], inv.size() * sizeof(R)));
-    CK(cudaMemcpy(pl->d_tw_fwd[vi], fwd.data(), fwd.size() * sizeof(R), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pl->d_tw_inv[vi], inv.data(), inv.size() * sizeof(R), cudaMemcpyHostToDevice));
+    std::vector<R> packed;
     if (pl->kind == WFB_R2C) {
         // W_n^k, k = 0..M (fft_split_native_f32.wat:1167-1191; fft_real_combined.wat:931-948)
         int rf = sizeof(R) == 8 ? ((pl->n == 8 || pl->n == 32) ? TW_EXACT : TW_F64) : TW_F32_SPLIT;
-        std::vector<R> rre, rim, packed;
+        std::vector<R> rre, rim;
         base_twiddles<R>(rf, pl->n, m + 1, rre, rim);
         for (int k = 0; k <= m; k++) { packed.push_back(rre[k]); packed.push_back(rim[k]); }
         widen(packed);
-        CK(cudaMalloc(&pl->d_rtw[vi], packed.size() * sizeof(R)));
-        CK(cudaMemcpy(pl->d_rtw[vi], packed.data(), packed.size() * sizeof(R), cudaMemcpyHostToDevice));
     }
+    // one allocation and one copy per variant: [forward | inverse | W_n^k], each 256-byte aligned
+    auto up256 = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t bf = up256(fwd.size() * sizeof(R)), bi = up256(inv.size() * sizeof(R)), br = up256(packed.size() * sizeof(R));
+    std::vector<unsigned char> blob(bf + bi + br, 0);
+    memcpy(blob.data(), fwd.data(), fwd.size() * sizeof(R));
+    memcpy(blob.data() + bf, inv.data(), inv.size() * sizeof(R));
+    if (!packed.empty()) memcpy(blob.data() + bf + bi, packed.data(), packed.size() * sizeof(R));
+    CK(cudaMalloc(&pl->d_tables[vi], blob.size()));
+    // stream-ordered on the plan's stream and completed here: launches on ANY stream may follow (plan streams are
+    // non-blocking, so the legacy-stream cudaMemcpy would not order against them)
+    CK(cudaMemcpyAsync(pl->d_tables[vi], blob.data(), blob.size(), cudaMemcpyHostToDevice, pl->stream));
+    CK(cudaStreamSynchronize(pl->stream));
+    pl->d_tw_fwd[vi] = pl->d_tables[vi];
+    pl->d_tw_inv[vi] = (unsigned char *)pl->d_tables[vi] + bf;
+    pl->d_rtw[vi] = packed.empty() ? nullptr : (unsigned char *)pl->d_tables[vi] + bf + bi;
     return WFB_OK;
 }
 
-static int plan_init(wfb_plan *pl) {
-    CK(cudaSetDevice(pl->device));
-    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+// Twiddle tables are per kernel variant (stage grouping and lane packing differ); only the variants that are actually
+// launched get theirs: the plan's defaults at creation (this is the reference's precompute_* call), the others on
+// their first launch.
+static int ensure_tables(wfb_plan *pl, int vi) {
+    if (pl->tables_ready[vi]) return WFB_OK;
+    int rc = pl->precision == WFB_F64 ? upload_tables<double>(pl, vi) : upload_tables<float>(pl, vi);
+    if (rc == WFB_OK) pl->tables_ready[vi] = true;
+    return rc;
+}
+
+static int ensure_device_buffers(wfb_plan *pl) {
+    if (pl->flags & WFB_PLAN_NO_DEVICE_BUFFERS) return WFB_OK;
+    for (int i = 0; i < 2; i++)
+        if (pl->bytes[i] && !pl->d_buf[i]) {
+            if (cudaMalloc(&pl->d_buf[i], pl->bytes[i]) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+        }
+    return WFB_OK;
+}
+
+static int ensure_pipeline(wfb_plan *pl) {
+    if (pl->pipe_ready) return WFB_OK;
     for (int i = 0; i < wfb_plan::NPIPE; i++) {
         CK(cudaStreamCreateWithFlags(&pl->pipe[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&pl->pipe_done[i], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&pl->start_ev, cudaEventDisableTiming));
-    for (size_t vi = 0; vi < pl->variants.size(); vi++) {
-        int rc = pl->precision == WFB_F64 ? upload_tables<double>(pl, (int)vi) : upload_tables<float>(pl, (int)vi);
-        if (rc) return rc;
-    }
+    pl->pipe_ready = true;
+    return WFB_OK;
+}
+
+static size_t payload_bytes(const wfb_plan *pl) {
+    const size_t e = pl->elem, n = (size_t)pl->n, b = (size_t)pl->batch;
+    if (pl->kind == WFB_C2C) return 2 * (2 * e * n) * b;          // one read + one write of n complex values
+    return (e * n + e * (n + 2)) * b;                               // n reals one way, n/2+1 bins the other
+}
+
+// true when wfb_exec(H2D | D2H) runs the zero-copy path: the kernel reads and writes the mapped host buffers directly
+static bool use_mapped(const wfb_plan *pl) {
+    return pl->hd_buf[0] && pl->mapped_variant >= 0 && (long)payload_bytes(pl) <= pl->mapped_max_bytes;
+}
+
+static long env_long(const char *name, long dflt) { const char *e = getenv(name); return e ? atol(e) : dflt; }
+
+static int plan_init(wfb_plan *pl) {
+    CK(cudaSetDevice(pl->device));
+    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     const size_t e = pl->elem, n = (size_t)pl->n, b = (size_t)pl->batch;
     if (pl->kind == WFB_C2C) {
         if (pl->layout == WFB_SPLIT) { pl->bytes[0] = pl->bytes[1] = e * n * b; }
@@ -334,23 +387,41 @@ static int plan_init(wfb_plan *pl) {
         pl->bytes[WFB_BUF_TIME] = e * n * b;
         pl->bytes[WFB_BUF_SPECTRUM] = e * (n + 2) * b;
     }
-    if (!(pl->flags & WFB_PLAN_NO_DEVICE_BUFFERS))
-        for (int i = 0; i < 2; i++)
-            if (pl->bytes[i]) { if (cudaMalloc(&pl->d_buf[i], pl->bytes[i]) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; } }
+    // staging knobs (wfb_plan_set_option overrides the environment defaults)
+    pl->mapped_max_bytes = env_long("WFB_MAPPED_MAX_KB", 256) << 10;
+    pl->stage_chunk_bytes = std::max(1L, env_long("WFB_STAGE_CHUNK_MB", 32)) << 20;
+    pl->stage_streams = (int)std::min<long>(wfb_plan::NPIPE, std::max(1L, env_long("WFB_STAGE_STREAMS", 3)));
+    // the zero-copy path launches the direct-load kernel (no TMA pipeline to fill, no tile counter): lowest alignment need
+    pl->mapped_variant = -1;
+    for (size_t i = 0; i < pl->variants.size(); i++)
+        if (pl->variants[i]->align < 16 && (pl->mapped_variant < 0 || pl->variants[i]->align < pl->variants[pl->mapped_variant]->align))
+            pl->mapped_variant = (int)i;
     if (!(pl->flags & WFB_PLAN_NO_HOST_BUFFERS)) {
+        // mapped + portable: the kernels can address these buffers directly (hd_buf), which is what the small-batch path does
+        const unsigned hf = cudaHostAllocMapped | cudaHostAllocPortable;
         if (pl->kind == WFB_R2C && pl->batch == 1) {
             // the reference's input and output views are the same bytes (index.js:136-141)
-            if (cudaHostAlloc(&pl->h_buf[1], pl->bytes[1], cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+            if (cudaHostAlloc(&pl->h_buf[1], pl->bytes[1], hf) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
             memset(pl->h_buf[1], 0, pl->bytes[1]);
             pl->h_buf[0] = pl->h_buf[1];
             pl->host_alias = true;
         } else {
             for (int i = 0; i < 2; i++)
                 if (pl->bytes[i]) {
-                    if (cudaHostAlloc(&pl->h_buf[i], pl->bytes[i], cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+                    if (cudaHostAlloc(&pl->h_buf[i], pl->bytes[i], hf) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
                     memset(pl->h_buf[i], 0, pl->bytes[i]);
                 }
         }
+        for (int i = 0; i < 2; i++)
+            if (pl->h_buf[i] && cudaHostGetDevicePointer(&pl->hd_buf[i], pl->h_buf[i], 0) != cudaSuccess) { cudaGetLastError(); pl->hd_buf[0] = pl->hd_buf[1] = nullptr; break; }
+    }
+    int rc;
+    if (use_mapped(pl)) {
+        // small plan: exec never leaves the mapped buffers; device buffers and the other variants' tables are made on demand
+        if ((rc = ensure_tables(pl, pl->mapped_variant))) return rc;
+    } else {
+        if ((rc = ensure_tables(pl, pl->variant)) || (rc = ensure_tables(pl, pl->variant_inv))) return rc;
+        if ((rc = ensure_device_buffers(pl))) return rc;
     }
     return WFB_OK;
 }
@@ -412,8 +483,7 @@ void wfb_plan_destroy(wfb_plan *pl) {
         if (pl->pipe_done[i]) cudaEventDestroy(pl->pipe_done[i]);
     }
     if (pl->start_ev) cudaEventDestroy(pl->start_ev);
-    for (int i = 0; i < 8; i++) { if (pl->d_tw_fwd[i]) cudaFree(pl->d_tw_fwd[i]); if (pl->d_tw_inv[i]) cudaFree(pl->d_tw_inv[i]); }
-    for (int i = 0; i < 8; i++) if (pl->d_rtw[i]) cudaFree(pl->d_rtw[i]);
+    for (int i = 0; i < 8; i++) if (pl->d_tables[i]) cudaFree(pl->d_tables[i]);
     for (int i = 0; i < 2; i++) if (pl->d_buf[i]) cudaFree(pl->d_buf[i]);
     if (pl->host_alias) { if (pl->h_buf[1]) cudaFreeHost(pl->h_buf[1]); }
     else for (int i = 0; i < 2; i++) if (pl->h_buf[i]) cudaFreeHost(pl->h_buf[i]);
@@ -421,7 +491,14 @@ void wfb_plan_destroy(wfb_plan *pl) {
 }
 
 void *wfb_host_buffer(wfb_plan *pl, int which) { return (pl && which >= 0 && which < 2) ? pl->h_buf[which] : nullptr; }
-void *wfb_device_buffer(wfb_plan *pl, int which) { return (pl && which >= 0 && which < 2) ? pl->d_buf[which] : nullptr; }
+void *wfb_device_buffer(wfb_plan *pl, int which) {
+    if (!pl || which < 0 || which >= 2) return nullptr;
+    if (!pl->d_buf[which] && pl->bytes[which]) {          // small plans allocate their device buffers on demand
+        cudaSetDevice(pl->device);
+        if (ensure_device_buffers(pl) != WFB_OK) return nullptr;
+    }
+    return pl->d_buf[which];
+}
 size_t wfb_host_bytes(wfb_plan *pl, int which) { return (pl && which >= 0 && which < 2) ? pl->bytes[which] : 0; }
 // C2C contexts are in place: the input view is the output view (index.js:78-83)
 void *wfb_host_in(wfb_plan *pl, int plane) { return wfb_host_buffer(pl, plane); }
@@ -433,6 +510,7 @@ int wfb_plan_set_variant(wfb_plan *pl, int v) {
     if (!pl || v < 0 || v >= (int)pl->variants.size()) return WFB_ERR_BAD_ARG;
     pl->variant = v;
     pl->variant_inv = v;
+    pl->mapped_max_bytes = 0;      // an explicitly chosen kernel is the kernel that runs: no zero-copy detour
     return WFB_OK;
 }
 int wfb_plan_current_variant(wfb_plan *pl, int direction) {
@@ -443,20 +521,38 @@ const char *wfb_plan_variant_name(wfb_plan *pl, int v) {
     if (!pl || v < 0 || v >= (int)pl->variants.size()) return "";
     return pl->variants[v]->name;
 }
-size_t wfb_plan_algorithmic_bytes(wfb_plan *pl) {
-    if (!pl) return 0;
-    const size_t e = pl->elem, n = (size_t)pl->n, b = (size_t)pl->batch;
-    if (pl->kind == WFB_C2C) return 2 * (2 * e * n) * b;          // one read + one write of n complex values
-    return (e * n + e * (n + 2)) * b;                               // n reals one way, n/2+1 bins the other
+size_t wfb_plan_algorithmic_bytes(wfb_plan *pl) { return pl ? payload_bytes(pl) : 0; }
+
+int wfb_plan_set_option(wfb_plan *pl, int option, long value) {
+    if (!pl || value < 0) return WFB_ERR_BAD_ARG;
+    switch (option) {
+        case WFB_OPT_MAPPED_MAX_BYTES: pl->mapped_max_bytes = value; return WFB_OK;
+        case WFB_OPT_STAGE_CHUNK_BYTES: if (value < 4096) return WFB_ERR_BAD_ARG; pl->stage_chunk_bytes = value; return WFB_OK;
+        case WFB_OPT_STAGE_STREAMS: if (value < 1 || value > wfb_plan::NPIPE) return WFB_ERR_BAD_ARG; pl->stage_streams = (int)value; return WFB_OK;
+        default: return WFB_ERR_BAD_ARG;
+    }
 }
+long wfb_plan_get_option(wfb_plan *pl, int option) {
+    if (!pl) return -1;
+    switch (option) {
+        case WFB_OPT_MAPPED_MAX_BYTES: return pl->mapped_max_bytes;
+        case WFB_OPT_STAGE_CHUNK_BYTES: return pl->stage_chunk_bytes;
+        case WFB_OPT_STAGE_STREAMS: return pl->stage_streams;
+        default: return -1;
+    }
+}
+int wfb_plan_last_path(wfb_plan *pl) { return pl ? pl->last_path : WFB_ERR_BAD_ARG; }
 unsigned long long wfb_kernel_launch_count(void) { return g_launches.load(); }
 
 // launches the current variant over `rows` rows starting at the given plane pointers
 static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void *in1, void *out0, void *out1,
-                       long rows, cudaStream_t s) {
-    int vi = direction == WFB_INVERSE ? pl->variant_inv : pl->variant;
+                       long rows, cudaStream_t s, int force_variant = -1) {
+    int vi = force_variant >= 0 ? force_variant : (direction == WFB_INVERSE ? pl->variant_inv : pl->variant);
     // The TMA / 128-bit kernels need 16-byte aligned planes (cudaMalloc gives 256).  Caller-supplied
     // pointers that are less aligned are served by the first variant whose requirement they meet.
+    // The second plane pointers only exist for split c2c; elsewhere whatever the caller left there is ignored.
+    const bool two_planes = pl->kind == WFB_C2C && pl->layout == WFB_SPLIT;
+    if (!two_planes) { in1 = nullptr; out1 = nullptr; }
     const uintptr_t bits = (uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)out0 | (uintptr_t)out1;
     auto need = [&](const Variant *v) {
         // direct kernels read split planes with scalar loads
@@ -470,6 +566,7 @@ static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void 
         vi = alt;
     }
     const Variant &v = *pl->variants[vi];
+    if (int rc = ensure_tables(pl, vi)) return rc;
     KParams p;
     p.in0 = in0; p.in1 = in1; p.out0 = out0; p.out1 = out1;
     p.tw = direction == WFB_INVERSE ? pl->d_tw_inv[vi] : pl->d_tw_fwd[vi];
@@ -510,7 +607,7 @@ int wfb_sync(wfb_plan *pl) {
 
 int wfb_exec(wfb_plan *pl, int direction, int flags) {
     if (!pl || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
-    if (!pl->d_buf[0]) return WFB_ERR_BAD_ARG;
+    if (pl->flags & WFB_PLAN_NO_DEVICE_BUFFERS) return WFB_ERR_BAD_ARG;
     if ((flags & (WFB_STAGE_H2D | WFB_STAGE_D2H)) && !pl->h_buf[0] && !pl->h_buf[1]) return WFB_ERR_NO_HOST_BUFFERS;
     CK(cudaSetDevice(pl->device));
     // buffer ids and per-row byte strides of the planes read and written
@@ -528,17 +625,32 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
         dst_row[0] = e * (a == WFB_BUF_TIME ? n + 2 : n);
     }
     const bool h2d = flags & WFB_STAGE_H2D, d2h = flags & WFB_STAGE_D2H;
-    // rows per pipeline chunk: ~16 MiB of the widest plane, so each copy is long enough to run at
+
+    // ---- zero-copy path (small payloads; the reference's own call shape is batch = 1, index.js:84-89): ONE launch of
+    // the direct-load kernel on the mapped host buffers -- the loads and stores cross PCIe themselves, so there is no
+    // copy node in front of or behind the kernel and nothing to wait for but the kernel.  In place is safe: every CTA of
+    // the direct kernels has all its rows in registers (behind a barrier for multi-pass plans) before its first store.
+    if (h2d && d2h && use_mapped(pl)) {
+        int rc = launch_rows(pl, direction, pl->hd_buf[src[0]], src[1] >= 0 ? pl->hd_buf[src[1]] : nullptr,
+                             pl->hd_buf[dst[0]], dst[1] >= 0 ? pl->hd_buf[dst[1]] : nullptr, pl->batch, pl->stream, pl->mapped_variant);
+        if (rc) return rc;
+        pl->last_path = WFB_PATH_MAPPED;
+        if (flags & WFB_SYNC) CK(cudaStreamSynchronize(pl->stream));
+        return WFB_OK;
+    }
+
+    if (int rc = ensure_device_buffers(pl)) return rc;
+    // rows per pipeline chunk: stage_chunk_bytes of the widest plane, so each copy is long enough to run at
     // full PCIe rate while there are enough chunks to overlap the two directions
     size_t widest = src_row[0] > dst_row[0] ? src_row[0] : dst_row[0];
-    static const long chunk_bytes = [] { const char *e = getenv("WFB_STAGE_CHUNK_MB"); long v = e ? atol(e) : 32; return (v < 1 ? 1 : v) << 20; }();
-    static const int nstreams = [] { const char *e = getenv("WFB_STAGE_STREAMS"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > wfb_plan::NPIPE ? (int)wfb_plan::NPIPE : v); }();
-    long chunk = (long)(chunk_bytes / (long)widest);
+    const int nstreams = pl->stage_streams;
+    long chunk = (long)(pl->stage_chunk_bytes / (long)widest);
     // whole tiles per chunk (tiles hold up to 256 rows) and 16-byte aligned chunk starts for the (n+2)-wide spectrum rows
     if (chunk >= 512) chunk &= ~255L; else if (chunk >= 2) chunk &= ~1L;
     if (chunk < 1) chunk = 1;
     const bool pipelined = (h2d || d2h) && pl->batch > 2 * chunk;
     if (!pipelined) {
+        pl->last_path = WFB_PATH_STAGED;
         if (h2d)
             for (int i = 0; i < 2; i++)
                 if (src[i] >= 0) CK(cudaMemcpyAsync(pl->d_buf[src[i]], pl->h_buf[src[i]], pl->bytes[src[i]], cudaMemcpyHostToDevice, pl->stream));
@@ -549,9 +661,13 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
             for (int i = 0; i < 2; i++)
                 if (dst[i] >= 0) CK(cudaMemcpyAsync(pl->h_buf[dst[i]], pl->d_buf[dst[i]], pl->bytes[dst[i]], cudaMemcpyDeviceToHost, pl->stream));
     } else {
+        pl->last_path = WFB_PATH_PIPELINED;
+        if (int rc = ensure_pipeline(pl)) return rc;
+        // the kernels of every chunk share one variant: its tables must exist before the first stream uses them
+        if (int rc = ensure_tables(pl, direction == WFB_INVERSE ? pl->variant_inv : pl->variant)) return rc;
         // order the pipeline after whatever is already queued on the plan's stream
         CK(cudaEventRecord(pl->start_ev, pl->stream));
-        for (int i = 0; i < wfb_plan::NPIPE; i++) CK(cudaStreamWaitEvent(pl->pipe[i], pl->start_ev, 0));
+        for (int i = 0; i < nstreams; i++) CK(cudaStreamWaitEvent(pl->pipe[i], pl->start_ev, 0));
         int c = 0;
         for (long r0 = 0; r0 < pl->batch; r0 += chunk, c++) {
             const long rows = (pl->batch - r0 < chunk) ? pl->batch - r0 : chunk;
@@ -570,12 +686,64 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
                 for (int i = 0; i < 2; i++)
                     if (dst[i] >= 0) CK(cudaMemcpyAsync((char *)pl->h_buf[dst[i]] + (size_t)r0 * dst_row[i], dout[i], (size_t)rows * dst_row[i], cudaMemcpyDeviceToHost, s));
         }
-        for (int i = 0; i < wfb_plan::NPIPE; i++) {
+        for (int i = 0; i < nstreams; i++) {
             CK(cudaEventRecord(pl->pipe_done[i], pl->pipe[i]));
             CK(cudaStreamWaitEvent(pl->stream, pl->pipe_done[i], 0));
         }
     }
     if (flags & WFB_SYNC) CK(cudaStreamSynchronize(pl->stream));
+    return WFB_OK;
+}
+
+// Pinned-copy ceiling of the link wfb_exec stages over: plain cudaMemcpyAsync between a pinned host buffer and the
+// device, each direction alone and both at once (one stream each), CUDA-event timed.  bench.py runs it on every rank
+// at the same moment, so the figure is the CONCURRENT ceiling of the box, the roofline of the e2e number.
+int wfb_pcie_probe(int device, size_t bytes, int iters, double gbs[4]) {
+    if (!gbs || bytes < 4096 || iters < 1) return WFB_ERR_BAD_ARG;
+    int rc = check_device(device);
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    void *h[2] = {nullptr, nullptr}, *d[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; i++) { if (h[i]) cudaFreeHost(h[i]); if (d[i]) cudaFree(d[i]); if (st[i]) cudaStreamDestroy(st[i]); }
+        for (int i = 0; i < 4; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+    };
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call); } } while (0)
+    for (int i = 0; i < 2; i++) {
+        CKP(cudaHostAlloc(&h[i], bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h[i], 0, bytes);
+        CKP(cudaMalloc(&d[i], bytes));
+        CKP(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    }
+    for (int i = 0; i < 4; i++) CKP(cudaEventCreate(&ev[i]));
+    auto run = [&](bool up, bool down, double *t_up, double *t_down) -> cudaError_t {
+        cudaError_t e;
+        for (int w = 0; w < 2; w++) {            // w = 0: warm-up pass
+            if (up) if ((e = cudaEventRecord(ev[0], st[0]))) return e;
+            if (down) if ((e = cudaEventRecord(ev[2], st[1]))) return e;
+            for (int i = 0; i < (w ? iters : 1); i++) {
+                if (up) if ((e = cudaMemcpyAsync(d[0], h[0], bytes, cudaMemcpyHostToDevice, st[0]))) return e;
+                if (down) if ((e = cudaMemcpyAsync(h[1], d[1], bytes, cudaMemcpyDeviceToHost, st[1]))) return e;
+            }
+            if (up) if ((e = cudaEventRecord(ev[1], st[0]))) return e;
+            if (down) if ((e = cudaEventRecord(ev[3], st[1]))) return e;
+            if ((e = cudaStreamSynchronize(st[0])) || (e = cudaStreamSynchronize(st[1]))) return e;
+        }
+        float ms;
+        if (up) { if ((e = cudaEventElapsedTime(&ms, ev[0], ev[1]))) return e; *t_up = ms * 1e-3; }
+        if (down) { if ((e = cudaEventElapsedTime(&ms, ev[2], ev[3]))) return e; *t_down = ms * 1e-3; }
+        return cudaSuccess;
+    };
+    double tu = 0, td = 0, tdu = 0, tdd = 0, dummy = 0;
+    CKP(run(true, false, &tu, &dummy));
+    CKP(run(false, true, &dummy, &td));
+    CKP(run(true, true, &tdu, &tdd));
+#undef CKP
+    const double gb = (double)bytes * iters / 1e9;
+    gbs[0] = gb / tu; gbs[1] = gb / td; gbs[2] = gb / tdu; gbs[3] = gb / tdd;
+    cleanup();
     return WFB_OK;
 }
 
@@ -700,6 +868,7 @@ int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void
     sp.frames = st->frames; sp.hop = st->hop; sp.wsize = st->wsize; sp.mode = st->mode & 0xFF;
     sp.db_floor = st->db_floor; sp.inv_range = st->inv_range; sp.inv_half_n = 2.0f / (float)st->fft_size;
     sp.ctr = nullptr;
+    sp.aligned8 = ((uintptr_t)d_samples % 8) == 0;      // a caller's pointer may be any float address (scalar loads then)
     // fast dB path: v = lg_a * log2(|2 X|^2) + lg_b  ==  (10 log10(|X|^2 c^2) - floor) / range,  c = 2 / fft_size
     sp.lg_a = 3.0102999566398120f * st->inv_range;
     sp.lg_b = sp.lg_a * (2.0f * log2f(sp.inv_half_n) - 2.0f) - st->db_floor * st->inv_range;

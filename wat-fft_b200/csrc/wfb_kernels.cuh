@@ -1875,6 +1875,7 @@ struct StftParams {
     float inv_half_n;          // 1 / (N/2)
     unsigned long long *ctr;   // pipelined kernel: zeroed tile counter of this launch
     float lg_a, lg_b;          // fast dB path: value = lg_a * log2(|2 X|^2) + lg_b (host-folded constants)
+    int aligned8;              // `samples` is 8-byte aligned: even hops may use 64-bit loads
 };
 enum { STFT_MODE_DB = 0, STFT_MODE_COMPLEX = 1 };
 // kernel flavours (template parameter KM): the dB output has a fast path that needs no square root and folds every
@@ -1959,7 +1960,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft(const __grid_constant__
 
     {   // gather + window + zero-pad: z[p] = (s[off+2p] w[2p], s[off+2p+1] w[2p+1])
         const float *s = sp.samples + (active ? frame * (long)sp.hop : 0);
-        const bool vec = ((sp.hop | sp.wsize) & 1) == 0;    // even hop: frame starts are 8-byte aligned
+        const bool vec = sp.aligned8 && ((sp.hop | sp.wsize) & 1) == 0;    // aligned base, even hop: frame starts are 8-byte aligned
         static_for<PL::E>([&](auto E_) {
             CIDX(e, E_);
             const int i0 = 2 * (tid + e * PL::T);
