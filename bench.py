@@ -605,7 +605,15 @@ def run_ours(args):
                "latency_us_copy_path": round(med_staged, 2),
                "plan_create_ms": round(statistics.median(t_create), 3),
                "max_err_over_norm_vs_oracle": err, "max_err_over_norm_vs_f64_dft": err_dft,
-               "Mtransforms_s": round(1.0 / med, 4)}
+               "Mtransforms_s": round(1.0 / med, 4),
+               "measured_through": "the Python mirror of the context API (ctypes call + two numpy view writes per call included)"}
+        # the same call sequence from C (tools/native/abi_latency.c): what the N-API shim sees, no host-language overhead
+        try:
+            exe = ROOT / "tools" / "native" / "abi_latency"
+            out = subprocess.run([str(exe), "1024", "1", "5000"], capture_output=True, text=True, timeout=120)
+            lat["native_c_abi"] = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as ex:                                 # the tool is optional evidence, never a reason to fail the bench
+            lat["native_c_abi"] = {"unavailable": repr(ex)}
 
     # ---- pinned-copy ceiling of the host link, all ranks at once (the roofline of the e2e number)
     gbs = (ctypes.c_double * 4)()

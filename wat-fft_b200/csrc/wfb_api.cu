@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -146,6 +147,63 @@ cudaError_t launch_persistent(const void *kernel, size_t smem, int threads, long
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------------------
+// Small-allocation pools.  cudaHostAlloc / cudaMalloc cost 0.1-1 ms each, and the reference's call shape is one small
+// context per transform size (createFFT(size), index.js:69-91): a batch-1 plan needs two 4-KB host views, a few KB of
+// tables and a completion flag.  Those come out of 4-MiB slabs (pinned + device-mapped + portable host memory; device
+// memory per GPU) with per-size free lists; only allocations above SMALL_MAX go to the driver directly.
+// ----------------------------------------------------------------------------------------
+struct SmallPool {
+    enum : size_t { SLAB = 4u << 20, SMALL_MAX = 256u << 10 };
+    bool host;
+    int device;
+    char *cur = nullptr;
+    size_t left = 0;
+    std::map<size_t, std::vector<void *>> free_lists;
+    static size_t round(size_t b) { return (b + 255) / 256 * 256; }
+    cudaError_t alloc(size_t bytes, void **out) {          // caller holds g_mu
+        const size_t r = round(bytes);
+        auto it = free_lists.find(r);
+        if (it != free_lists.end() && !it->second.empty()) { *out = it->second.back(); it->second.pop_back(); return cudaSuccess; }
+        if (left < r) {
+            void *slab = nullptr;
+            cudaError_t e = host ? cudaHostAlloc(&slab, SLAB, cudaHostAllocMapped | cudaHostAllocPortable) : cudaMalloc(&slab, SLAB);
+            if (e != cudaSuccess) return e;
+            cur = (char *)slab; left = SLAB;              // (the tail of the previous slab stays unused)
+        }
+        *out = cur; cur += r; left -= r;
+        return cudaSuccess;
+    }
+    void release(void *p, size_t bytes) { free_lists[round(bytes)].push_back(p); }
+};
+static SmallPool g_host_pool{true, -1};
+static std::map<int, SmallPool> g_dev_pools;
+
+static cudaError_t host_alloc(size_t bytes, void **out) {
+    if (bytes > SmallPool::SMALL_MAX) return cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    std::lock_guard<std::mutex> lock(g_mu);
+    return g_host_pool.alloc(bytes, out);
+}
+static void host_free(void *p, size_t bytes) {
+    if (!p) return;
+    if (bytes > SmallPool::SMALL_MAX) { cudaFreeHost(p); return; }
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_host_pool.release(p, bytes);
+}
+static cudaError_t dev_alloc(int device, size_t bytes, void **out) {
+    if (bytes > SmallPool::SMALL_MAX) return cudaMalloc(out, bytes);
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_dev_pools.find(device);
+    if (it == g_dev_pools.end()) it = g_dev_pools.emplace(device, SmallPool{false, device}).first;
+    return it->second.alloc(bytes, out);
+}
+static void dev_free(int device, void *p, size_t bytes) {
+    if (!p) return;
+    if (bytes > SmallPool::SMALL_MAX) { cudaFree(p); return; }
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_dev_pools.find(device)->second.release(p, bytes);
+}
+
 static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
 static int ilog2(long n) { int k = 0; while ((1L << k) < n) k++; return k; }
 
@@ -167,6 +225,7 @@ struct wfb_plan {
     void *d_tw_fwd[8], *d_tw_inv[8];   // per variant; built and uploaded on the variant's first launch (ensure_tables)
     void *d_rtw[8];                    // per variant (table format depends on the lane type)
     void *d_tables[8];                 // the one allocation d_tw_fwd / d_tw_inv / d_rtw of a variant point into
+    size_t tables_bytes[8];
     bool tables_ready[8];
     std::vector<unsigned char> h_tw0_fwd[8], h_tw0_inv[8];   // head of each table for KParams::tw0 (scalar-lane variants)
     // buffers: C2C -> plane 0 / plane 1; R2C -> time / spectrum
@@ -180,6 +239,11 @@ struct wfb_plan {
     long stage_chunk_bytes;            // staging pipeline: bytes of the widest plane per chunk
     int stage_streams;                 // ... and the number of streams the chunks cycle over
     int last_path;                     // WFB_PATH_* of the latest wfb_exec
+    // completion flag of the zero-copy path: the kernel's last act is a store of `token` to this word of mapped host
+    // memory (after a system-scope fence behind its data stores); wfb_exec polls it instead of calling into the driver
+    volatile unsigned *h_flag;
+    unsigned *hd_flag, *d_done_ctr;
+    unsigned token;
     cudaStream_t stream;
     // staging pipeline: chunks of rows cycle over these streams so the H2D copy of chunk c+1, the
     // kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex)
@@ -189,7 +253,20 @@ struct wfb_plan {
     bool pipe_ready;                   // streams / events above exist (created by the first pipelined exec)
 };
 
+static int check_device_uncached(int device);
+// cudaGetDeviceProperties costs milliseconds; a plan is created per transform size, so the verdict is cached per device
 static int check_device(int device) {
+    static std::map<int, int> ok;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = ok.find(device);
+        if (it != ok.end()) return it->second;
+    }
+    const int rc = check_device_uncached(device);
+    if (rc == WFB_OK) { std::lock_guard<std::mutex> lock(g_mu); ok[device] = rc; }
+    return rc;
+}
+static int check_device_uncached(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
@@ -322,7 +399,8 @@ static int upload_tables(wfb_plan *pl, int vi) {
     memcpy(blob.data(), fwd.data(), fwd.size() * sizeof(R));
     memcpy(blob.data() + bf, inv.data(), inv.size() * sizeof(R));
     if (!packed.empty()) memcpy(blob.data() + bf + bi, packed.data(), packed.size() * sizeof(R));
-    CK(cudaMalloc(&pl->d_tables[vi], blob.size()));
+    pl->tables_bytes[vi] = blob.size();
+    CK(dev_alloc(pl->device, blob.size(), &pl->d_tables[vi]));
     // stream-ordered on the plan's stream and completed here: launches on ANY stream may follow (plan streams are
     // non-blocking, so the legacy-stream cudaMemcpy would not order against them)
     CK(cudaMemcpyAsync(pl->d_tables[vi], blob.data(), blob.size(), cudaMemcpyHostToDevice, pl->stream));
@@ -347,7 +425,7 @@ static int ensure_device_buffers(wfb_plan *pl) {
     if (pl->flags & WFB_PLAN_NO_DEVICE_BUFFERS) return WFB_OK;
     for (int i = 0; i < 2; i++)
         if (pl->bytes[i] && !pl->d_buf[i]) {
-            if (cudaMalloc(&pl->d_buf[i], pl->bytes[i]) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+            if (dev_alloc(pl->device, pl->bytes[i], &pl->d_buf[i]) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
         }
     return WFB_OK;
 }
@@ -394,26 +472,40 @@ static int plan_init(wfb_plan *pl) {
     // the zero-copy path launches the direct-load kernel (no TMA pipeline to fill, no tile counter): lowest alignment need
     pl->mapped_variant = -1;
     for (size_t i = 0; i < pl->variants.size(); i++)
-        if (pl->variants[i]->align < 16 && (pl->mapped_variant < 0 || pl->variants[i]->align < pl->variants[pl->mapped_variant]->align))
-            pl->mapped_variant = (int)i;
+        if (pl->variants[i]->direct && pl->variants[i]->lanes == 1) { pl->mapped_variant = (int)i; break; }
     if (!(pl->flags & WFB_PLAN_NO_HOST_BUFFERS)) {
         // mapped + portable: the kernels can address these buffers directly (hd_buf), which is what the small-batch path does
-        const unsigned hf = cudaHostAllocMapped | cudaHostAllocPortable;
         if (pl->kind == WFB_R2C && pl->batch == 1) {
             // the reference's input and output views are the same bytes (index.js:136-141)
-            if (cudaHostAlloc(&pl->h_buf[1], pl->bytes[1], hf) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+            if (host_alloc(pl->bytes[1], &pl->h_buf[1]) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
             memset(pl->h_buf[1], 0, pl->bytes[1]);
             pl->h_buf[0] = pl->h_buf[1];
             pl->host_alias = true;
         } else {
             for (int i = 0; i < 2; i++)
                 if (pl->bytes[i]) {
-                    if (cudaHostAlloc(&pl->h_buf[i], pl->bytes[i], hf) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
+                    if (host_alloc(pl->bytes[i], &pl->h_buf[i]) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
                     memset(pl->h_buf[i], 0, pl->bytes[i]);
                 }
         }
         for (int i = 0; i < 2; i++)
             if (pl->h_buf[i] && cudaHostGetDevicePointer(&pl->hd_buf[i], pl->h_buf[i], 0) != cudaSuccess) { cudaGetLastError(); pl->hd_buf[0] = pl->hd_buf[1] = nullptr; break; }
+        // completion flag (host word) + CTA counter (device word) of the zero-copy path
+        void *f = nullptr, *c = nullptr;
+        if (pl->hd_buf[0] && host_alloc(256, &f) == cudaSuccess && dev_alloc(pl->device, 256, &c) == cudaSuccess) {
+            pl->h_flag = (volatile unsigned *)f;
+            *pl->h_flag = 0;
+            pl->d_done_ctr = (unsigned *)c;
+            if (cudaHostGetDevicePointer((void **)&pl->hd_flag, f, 0) != cudaSuccess ||
+                cudaMemsetAsync(c, 0, 256, pl->stream) != cudaSuccess || cudaStreamSynchronize(pl->stream) != cudaSuccess) {
+                cudaGetLastError();
+                pl->hd_flag = nullptr;
+            }
+        } else {
+            cudaGetLastError();
+            if (f) host_free(f, 256);
+            if (c) dev_free(pl->device, c, 256);
+        }
     }
     int rc;
     if (use_mapped(pl)) {
@@ -483,10 +575,12 @@ void wfb_plan_destroy(wfb_plan *pl) {
         if (pl->pipe_done[i]) cudaEventDestroy(pl->pipe_done[i]);
     }
     if (pl->start_ev) cudaEventDestroy(pl->start_ev);
-    for (int i = 0; i < 8; i++) if (pl->d_tables[i]) cudaFree(pl->d_tables[i]);
-    for (int i = 0; i < 2; i++) if (pl->d_buf[i]) cudaFree(pl->d_buf[i]);
-    if (pl->host_alias) { if (pl->h_buf[1]) cudaFreeHost(pl->h_buf[1]); }
-    else for (int i = 0; i < 2; i++) if (pl->h_buf[i]) cudaFreeHost(pl->h_buf[i]);
+    for (int i = 0; i < 8; i++) dev_free(pl->device, pl->d_tables[i], pl->tables_bytes[i]);
+    for (int i = 0; i < 2; i++) dev_free(pl->device, pl->d_buf[i], pl->bytes[i]);
+    if (pl->host_alias) host_free(pl->h_buf[1], pl->bytes[1]);
+    else for (int i = 0; i < 2; i++) host_free(pl->h_buf[i], pl->bytes[i]);
+    if (pl->h_flag) host_free((void *)pl->h_flag, 256);
+    if (pl->d_done_ctr) dev_free(pl->device, pl->d_done_ctr, 256);
     delete pl;
 }
 
@@ -546,7 +640,7 @@ unsigned long long wfb_kernel_launch_count(void) { return g_launches.load(); }
 
 // launches the current variant over `rows` rows starting at the given plane pointers
 static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void *in1, void *out0, void *out1,
-                       long rows, cudaStream_t s, int force_variant = -1) {
+                       long rows, cudaStream_t s, int force_variant = -1, bool signal = false) {
     int vi = force_variant >= 0 ? force_variant : (direction == WFB_INVERSE ? pl->variant_inv : pl->variant);
     // The TMA / 128-bit kernels need 16-byte aligned planes (cudaMalloc gives 256).  Caller-supplied
     // pointers that are less aligned are served by the first variant whose requirement they meet.
@@ -574,6 +668,9 @@ static int launch_rows(wfb_plan *pl, int direction, const void *in0, const void 
     p.batch = rows;
     p.scale = 1.0 / (double)pl->n;
     p.ctr = nullptr;
+    p.done_flag = signal ? pl->hd_flag : nullptr;
+    p.done_ctr = pl->d_done_ctr;
+    p.done_token = pl->token;
     const std::vector<unsigned char> &h0 = direction == WFB_INVERSE ? pl->h_tw0_inv[vi] : pl->h_tw0_fwd[vi];
     if (!h0.empty()) memcpy(p.tw0, h0.data(), KParams::TW0_BYTES);
     cudaError_t e;
@@ -631,11 +728,28 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
     // copy node in front of or behind the kernel and nothing to wait for but the kernel.  In place is safe: every CTA of
     // the direct kernels has all its rows in registers (behind a barrier for multi-pass plans) before its first store.
     if (h2d && d2h && use_mapped(pl)) {
+        const bool flagged = (flags & WFB_SYNC) && pl->hd_flag;
+        if (flagged) pl->token++;
         int rc = launch_rows(pl, direction, pl->hd_buf[src[0]], src[1] >= 0 ? pl->hd_buf[src[1]] : nullptr,
-                             pl->hd_buf[dst[0]], dst[1] >= 0 ? pl->hd_buf[dst[1]] : nullptr, pl->batch, pl->stream, pl->mapped_variant);
+                             pl->hd_buf[dst[0]], dst[1] >= 0 ? pl->hd_buf[dst[1]] : nullptr, pl->batch, pl->stream, pl->mapped_variant, flagged);
         if (rc) return rc;
         pl->last_path = WFB_PATH_MAPPED;
-        if (flags & WFB_SYNC) CK(cudaStreamSynchronize(pl->stream));
+        if (flagged) {
+            // the results are in host memory when the token is: no driver call on the way back.  The stream is consulted
+            // only if the token is late (a faulting kernel never writes it).
+            const unsigned want = pl->token;
+            auto t0 = std::chrono::steady_clock::now();
+            for (unsigned spins = 0; *pl->h_flag != want; spins++) {
+                __builtin_ia32_pause();
+                if ((spins & 0xFFF) == 0xFFF && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) {
+                    CK(cudaStreamSynchronize(pl->stream));       // also surfaces a kernel fault as an error code
+                    break;
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        } else if (flags & WFB_SYNC) {
+            CK(cudaStreamSynchronize(pl->stream));
+        }
         return WFB_OK;
     }
 

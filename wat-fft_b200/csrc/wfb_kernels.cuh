@@ -401,6 +401,10 @@ struct KParams {
     long batch;
     double scale;              // applied on store (1/N for the inverse c2c)
     unsigned long long *ctr;   // persistent kernels: this launch's counter pair {tile claims, departed CTAs}, zero on entry AND on exit
+    // zero-copy path (direct kernels on mapped host buffers): when done_flag is set, the last CTA to finish stores
+    // done_token there -- a word of mapped HOST memory the caller polls -- behind a system-scope fence
+    unsigned *done_flag, *done_ctr;
+    unsigned done_token;
     // the first TW0_BYTES of the stage table `tw` (scalar-lane variants): pass 0's thread-independent twiddles,
     // read as constant-bank operands (see CTw)
     enum { TW0_BYTES = 1008 };                         // 63 entries of a radix-64 opening pass in f64
@@ -421,6 +425,27 @@ template <typename R, class PL> struct UTw {
 };
 
 enum IoMode { IO_SPLIT = 0, IO_INTERLEAVED = 1 };
+
+// Completion signal of the zero-copy path.  Every thread fences its own stores to the mapped host buffers at system
+// scope, the CTA meets at a barrier, and the last CTA of the grid (device-memory counter, left at zero again) publishes
+// the token: a host thread that reads the token then reads the results (PCIe posted writes keep their order).
+// All threads of the CTA must call this (no early return before it).
+__device__ __forceinline__ void signal_done(const KParams &p) {
+    if (p.done_flag == nullptr) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool last = true;
+        if (gridDim.x > 1) {
+            last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1;
+            if (last) *p.done_ctr = 0u;
+        }
+        if (last) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(p.done_flag) = p.done_token;
+        }
+    }
+}
 
 // streaming global accesses: every payload byte is touched exactly once
 template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
@@ -537,6 +562,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c(const __grid_constant__ 
             });
         }
     }
+    signal_done(p);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -611,8 +637,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(const __grid_constant__ 
     if (PL::npass() > 1) sync_transform<PL::T, X>(g.xi);
     spill_outputs<R, PL, LAST, PADQ>(x, sm, tid);
     sync_transform<PL::T, X>(g.xi);
-    if (!g.active) return;
-
+    if (g.active) {
     V2 *out = reinterpret_cast<V2 *>(p.out0) + g.row * (M + 1);
     const long rs = g.lane1 * (M + 1);
     // pairs (k, M-k), k = tid + i*T over 0 .. M/2-1; k = 0 is DC/Nyquist; thread 0 adds k = M/2
@@ -638,6 +663,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(const __grid_constant__ 
             }
         }
     });
+    }
+    signal_done(p);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -704,6 +731,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2r(const __grid_constant__ 
             GIO<R>::st_il(z + e * PL::T, g.lane1 * M, g.two, x[slot]);
         });
     }
+    signal_done(p);
 }
 
 

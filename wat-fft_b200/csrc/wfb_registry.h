@@ -26,6 +26,7 @@ struct Variant {
                        // one complex value for the direct kernels (one scalar when the layout is split)
     std::vector<int> radices;
     launch_fn c2c, r2c, c2r;
+    bool direct = false;   // plain global loads/stores, one launch-sized grid (no TMA pipeline, no tile counter): the zero-copy path's kernel
 };
 
 // implemented in wfb_api.cu (one launch counter / attribute cache for the whole library)
@@ -73,7 +74,7 @@ template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers
         return launch_grid((const void *)k_c2r<R, PL, X, PADQ, MINB>, smem, PL::T * X, ctas(batch), p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
-        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 2 * (int)sizeof(typename RT<R>::scalar), plan_radices<PL>(), &c2c, &r2c, &c2r};
+        return Variant{name, PL::N, PL::T * X, X, smem, LANES, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 2 * (int)sizeof(typename RT<R>::scalar), plan_radices<PL>(), &c2c, &r2c, &c2r, true};
     }
 };
 
