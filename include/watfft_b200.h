@@ -117,6 +117,20 @@ WFB_API int wfb_exec(wfb_plan *plan, int direction, int flags);
 WFB_API int wfb_exec_device(wfb_plan *plan, int direction, const void *const d_in[2], void *const d_out[2],
                             void *stream);
 WFB_API int wfb_sync(wfb_plan *plan);
+
+/* ---- module-shaped host memory (the exports facade) -----------------------------------------------------------------
+ * The reference's raw exports work on ONE linear memory per instance: callers write inputs into `exports.memory.buffer`
+ * at the module's offsets, call fft_split(n) / fft(n) / rfft(n), and read the results from the same bytes
+ * (tests/fft_split_native.test.js:78-114; memory maps in modules/fft_split_native_f32.wat:7-18).  wfb_host_alloc returns
+ * such a memory: pinned, device-mapped host bytes (zeroed) that the JS side wraps as `memory.buffer`; wfb_exec_host runs a
+ * plan on plane pointers INSIDE memories obtained from wfb_host_alloc (anything else is WFB_ERR_BAD_ARG).  Small
+ * payloads (WFB_OPT_MAPPED_MAX_BYTES) are transformed in place by one kernel that reads and writes those bytes directly --
+ * no copy in either direction, like the WASM module working on its linear memory; larger ones are staged through the
+ * plan's device buffers.  h_in/h_out: two plane pointers (second unused unless C2C SPLIT); in == out is allowed for C2C
+ * and for R2C at batch = 1.  H2D/D2H staging is implied; flags adds WFB_SYNC (or not). */
+WFB_API void *wfb_host_alloc(size_t bytes);
+WFB_API void wfb_host_free(void *memory);
+WFB_API int wfb_exec_host(wfb_plan *plan, int direction, const void *const h_in[2], void *const h_out[2], int flags);
 WFB_API void *wfb_plan_stream(wfb_plan *plan);
 
 /* ---- introspection / tuning ------------------------------------------- */

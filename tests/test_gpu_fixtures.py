@@ -165,11 +165,13 @@ def test_context_contract(wf):
 
 
 def test_exports_facade(wf):
-    """The exports-shaped facade runs the reference's raw-export call sequence unchanged."""
-    ex = wf.SplitExportsFacade("fft_split_native_f32")
+    """The exports-shaped instance runs the reference's raw-export call sequence unchanged and SYNCHRONOUSLY: results are
+    in `memory` on the line after the call (tests/fft_split_native.test.js:78-114)."""
+    ex = wf.createFFTf32SplitInstance()
+    assert wf.SplitExportsFacade is wf.ModuleExports
     n = 1024
-    re = np.frombuffer(ex.memory, np.float32, n, ex.REAL_OFFSET)
-    im = np.frombuffer(ex.memory, np.float32, n, ex.IMAG_OFFSET)
+    re = np.frombuffer(ex.memory.buffer, np.float32, n, ex.REAL_OFFSET)
+    im = np.frombuffer(ex.memory.buffer, np.float32, n, ex.IMAG_OFFSET)
     rng = np.random.default_rng(1)
     a, b = rng.uniform(-1, 1, n).astype(np.float32), rng.uniform(-1, 1, n).astype(np.float32)
     re[:], im[:] = a, b
@@ -179,7 +181,74 @@ def test_exports_facade(wf):
     assert np.max(np.abs((re + 1j * im) - truth)) < 5e-3
     ex.ifft_split(n)
     assert np.max(np.abs(re - a)) < 1e-4
+    # precompute with a new n silently re-targets the instance (tests/boundary.test.js:304-332)
+    ex.precompute_rfft_twiddles_split(64)
+    x = np.frombuffer(ex.memory.buffer, np.float32, 66, 0)
+    sig = rng.uniform(-1, 1, 64).astype(np.float32)
+    x[:64] = sig
+    ex.rfft_split(64)
+    assert np.max(np.abs((x[0::2] + 1j * x[1::2]) - np.fft.rfft(sig.astype(np.float64)))) < 1e-4
+    ex.irfft_split(64)
+    assert np.max(np.abs(x[:64] - sig)) < 1e-5
     ex.dispose()
+
+
+@pytest.mark.parametrize("factory,dtype,real", [("createFFTInstance", np.float64, False), ("createFFTf32Instance", np.float32, False),
+                                                 ("createRFFTInstance", np.float64, True), ("createRFFTf32Instance", np.float32, True)])
+def test_instance_factories(wf, factory, dtype, real):
+    """index.js:28-58: the four low-level factories return raw module-shaped exports over one linear memory."""
+    ex = getattr(wf, factory)()
+    n = 256
+    rng = np.random.default_rng(3)
+    tol = 1e-12 if dtype == np.float64 else 2e-4
+    if real:
+        ex.precompute_rfft_twiddles(n)
+        buf = np.frombuffer(ex.memory.buffer, dtype, n + 2, 0)
+        sig = rng.uniform(-1, 1, n).astype(dtype)
+        buf[:n] = sig
+        ex.rfft(n)
+        assert np.max(np.abs((buf[0::2] + 1j * buf[1::2]) - np.fft.rfft(sig.astype(np.float64)))) < tol * n
+        ex.irfft(n)                         # (f64: extension, the reference export is missing)
+        assert np.max(np.abs(buf[:n] - sig)) < tol
+    else:
+        ex.precompute_twiddles(n)
+        buf = np.frombuffer(ex.memory.buffer, dtype, 2 * n, 0)
+        z = rng.uniform(-1, 1, 2 * n).astype(dtype)
+        buf[:] = z
+        ex.fft(n)
+        assert np.max(np.abs((buf[0::2] + 1j * buf[1::2]) - np.fft.fft(z[0::2].astype(np.float64) + 1j * z[1::2]))) < tol * n
+        ex.ifft(n)
+        assert np.max(np.abs(buf - z)) < tol
+    ex.dispose()
+
+
+def test_context_exports_field(wf):
+    """index.js:72-75: a context carries `exports`, the instance it runs on -- at batch = 1 the context's views ARE views of
+    exports.memory and forward() IS exports.fft(size); dispose() is idempotent and later use raises."""
+    n = 128
+    ctx = wf.createFFT(n)
+    ex = ctx.exports
+    view = np.frombuffer(ex.memory.buffer, np.float64, 2 * n, 0)
+    ctx.getInputBuffer()[:] = 0.0
+    ctx.getInputBuffer()[0] = 1.0                       # impulse through the context's view ...
+    assert view[0] == 1.0                               # ... is the instance's memory
+    ex.fft(n)                                           # raw export call
+    assert np.allclose(ctx.getOutputBuffer()[0::2], 1.0) and np.allclose(ctx.getOutputBuffer()[1::2], 0.0)
+    ctx.inverse()
+    assert abs(view[0] - 1.0) < 1e-15 and np.max(np.abs(view[1:])) < 1e-15
+    ctx.dispose()
+    ctx.dispose()
+    with pytest.raises(RuntimeError):
+        ctx.forward()
+    with pytest.raises(RuntimeError):
+        ctx.getInputBuffer()
+    big = wf.createRFFTf32(64, batch=4)                 # batch > 1: exports is a module instance of its own
+    e2 = big.exports
+    e2.precompute_rfft_twiddles(64)
+    np.frombuffer(e2.memory.buffer, np.float32, 64, 0)[:] = 1.0
+    e2.rfft(64)
+    assert abs(np.frombuffer(e2.memory.buffer, np.float32, 2, 0)[0] - 64.0) < 1e-4
+    big.dispose()
 
 
 def test_staged_pipeline_large_batch(wf, oracle):

@@ -93,7 +93,9 @@ def test_zero_copy_interleaved_and_f64(wf, oracle, n):
     assert c.plan.last_path() == C.PATH_MAPPED
     assert rel_err(c.getOutputBuffer(), oracle.fft_f64(z), z) <= f64_bound(n)
     c.inverse()
-    assert np.max(np.abs(c.getOutputBuffer() - z)) < 1e-13
+    # (the reference's f64 twiddles are a Taylor series good to ~5e-11 -- BASELINE.md section 1 -- so fft -> ifft is not the
+    #  identity to machine precision; sizes 4 and 16 use exact constants)
+    assert np.max(np.abs(c.getOutputBuffer() - z)) < (1e-13 if n <= 16 else 1e-9)
     c.dispose()
     if n >= 8:
         x = rng.uniform(-1, 1, n)

@@ -104,3 +104,48 @@ def test_gpu_spectrogram_errors_and_long_signal(wf, oracle):
     for f in (0, 1, frames // 2, frames - 1):
         ref = om.spectrogram_reference(x[f * 64: f * 64 + 1024], 1024, 64, rfft=oracle.rfft_split_f32)
         assert np.max(np.abs(g[f] - ref[0])) < 2e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_fft,zp", [(256, 1), (512, 1), (1024, 1), (1024, 2), (2048, 1), (4096, 1), (4096, 4), (8192, 1)])
+def test_span_kernel_many_tiles(wf, oracle, monkeypatch, n_fft, zp):
+    """The span-staged persistent kernel with enough frames that every CTA loops over several tiles and the last tile is
+    ragged: sampled frames against the reference loop, the whole picture against the direct kernel (different core plan,
+    same contract), and bitwise repeatability of the persistent schedule."""
+    hop = n_fft // zp // 4
+    frames_wanted = 9001 if n_fft <= 1024 else 3001
+    ns = (frames_wanted - 1) * hop + n_fft // zp + 3
+    x = _signal(ns, seed=n_fft + zp)
+    monkeypatch.setenv("WFB_STFT_SPAN", "1")
+    got = wf.generateSpectrogram(x, 16000.0, n_fft, hop, "hann", zp, gain=-3.0, range=75.0)
+    again = wf.generateSpectrogram(x, 16000.0, n_fft, hop, "hann", zp, gain=-3.0, range=75.0)
+    monkeypatch.setenv("WFB_STFT_SPAN", "0")
+    direct = wf.generateSpectrogram(x, 16000.0, n_fft, hop, "hann", zp, gain=-3.0, range=75.0)
+    f, b = got["numFrames"], got["numBins"]
+    assert f == frames_wanted and b == n_fft // 2 + 1
+    g, d = got["data"].reshape(f, b), direct["data"].reshape(f, b)
+    assert np.array_equal(g, again["data"].reshape(f, b))
+    assert np.max(np.abs(g - d)) < 2e-4
+    w = n_fft // zp
+    for fr in (0, 1, 7, 8, f // 2, f - 9, f - 2, f - 1):
+        ref = om.spectrogram_reference(x[fr * hop: fr * hop + w], n_fft, hop, "hann", zp, gain=-3.0, range_db=75.0,
+                                       rfft=oracle.rfft_split_f32)
+        assert np.max(np.abs(g[fr] - ref[0])) < 2e-4, fr
+
+
+@pytest.mark.gpu
+def test_span_kernel_complex_output(wf, oracle, monkeypatch):
+    n_fft, hop = 1024, 256
+    ns = 4000 * hop + n_fft
+    x = _signal(ns, seed=5)
+    monkeypatch.setenv("WFB_STFT_SPAN", "1")
+    sp = wf.Spectrogram(ns, n_fft, hop, "blackman", mode="complex")
+    sp.getInputBuffer()[:] = x
+    sp.run()
+    g = sp.getOutputBuffer().copy()
+    sp.dispose()
+    w = om.window_function("blackman", n_fft)
+    for fr in (0, 3, 2000, g.shape[0] - 1):
+        frame = (x[fr * hop: fr * hop + n_fft].astype(np.float64) * w).astype(np.float32)
+        ref = oracle.rfft_split_f32(frame).reshape(-1, 2)
+        assert np.max(np.abs(g[fr] - ref)) <= f32_bound(n_fft) * np.linalg.norm(frame), fr

@@ -10,11 +10,13 @@ from ._cabi import WatFFTError, build
 from .stft import Spectrogram, generateSpectrogram
 from .contexts import (
     createFFT, createFFTf32, createRFFT, createRFFTf32,
-    createFFTf32Split, createRFFTf32Split, SplitExportsFacade, Plan,
+    createFFTf32Split, createRFFTf32Split, SplitExportsFacade, ModuleExports, HostMemory, Plan,
+    createFFTInstance, createFFTf32Instance, createRFFTInstance, createRFFTf32Instance, createFFTf32SplitInstance,
 )
 
 __all__ = [
     "createFFT", "createFFTf32", "createRFFT", "createRFFTf32",
-    "createFFTf32Split", "createRFFTf32Split", "SplitExportsFacade", "Plan",
+    "createFFTf32Split", "createRFFTf32Split", "SplitExportsFacade", "ModuleExports", "HostMemory", "Plan",
+    "createFFTInstance", "createFFTf32Instance", "createRFFTInstance", "createRFFTf32Instance", "createFFTf32SplitInstance",
     "Spectrogram", "generateSpectrogram", "WatFFTError", "build", "_cabi",
 ]

@@ -47,6 +47,10 @@ SYMBOLS = {
     "wfb_exec_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                        ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
     "wfb_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "wfb_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "wfb_host_free": (None, [ctypes.c_void_p]),
+    "wfb_exec_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                     ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "wfb_plan_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "wfb_plan_variant_count": (ctypes.c_int, [ctypes.c_void_p]),
     "wfb_plan_set_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -8,8 +8,12 @@
 Semantics kept from the reference at batch = 1: complex contexts are in place (input and output
 views are the same bytes, index.js:78-83); real contexts read `size` reals and write
 (size/2+1)*2 interleaved values over the same bytes (index.js:136-141); forward()/inverse() are
-synchronous and return nothing.  New: `batch` (rows are contiguous per transform), `dispose()`,
-and creation raises WatFFTError when no B200 is present (no CPU fallback).
+synchronous and return nothing; every context carries `exports`, the raw module-shaped instance it
+runs on (index.js:72-75), and the four create*Instance() factories return such instances
+(index.js:28-58).  At batch = 1 a context is built exactly like the reference builds it: instance ->
+precompute(size) -> typed views over `exports.memory` -> forward() = exports.fft(size).
+New: `batch` (rows are contiguous per transform), `dispose()`, and creation raises WatFFTError when
+no B200 is present (no CPU fallback).  This file and js/index.js are the same design twice.
 """
 from __future__ import annotations
 
@@ -59,6 +63,12 @@ class Plan:
         b = (ctypes.c_void_p * 2)(*[ctypes.c_void_p(x) if x else None for x in d_out])
         C.check(self._lib.wfb_exec_device(self._p, direction, a, b, ctypes.c_void_p(stream) if stream else None))
 
+    def exec_host(self, direction, h_in, h_out, flags=C.SYNC):
+        """run on plane pointers inside a HostMemory (wfb_host_alloc): the exports facade's path"""
+        a = (ctypes.c_void_p * 2)(*[ctypes.c_void_p(x) if x else None for x in h_in])
+        b = (ctypes.c_void_p * 2)(*[ctypes.c_void_p(x) if x else None for x in h_out])
+        C.check(self._lib.wfb_exec_host(self._p, direction, a, b, flags))
+
     def sync(self):
         C.check(self._lib.wfb_sync(self._p))
 
@@ -102,63 +112,285 @@ class Plan:
             pass
 
 
-class _ComplexContext:
-    """createFFT / createFFTf32 shape: {size, getInputBuffer, getOutputBuffer, forward, inverse}."""
+class HostMemory:
+    """`exports.memory`: one module-sized block of pinned, device-mapped host memory (wfb_host_alloc).  `.buffer` is the
+    byte view (the JS side hands out the same bytes as an ArrayBuffer)."""
+
+    def __init__(self, nbytes):
+        self._lib = C.lib()
+        self.ptr = self._lib.wfb_host_alloc(nbytes)
+        if not self.ptr:
+            rc = self._lib.wfb_require_b200(0)
+            raise C.WatFFTError(rc if rc else C.ERR_ALLOC)
+        self.nbytes = nbytes
+        self.buffer = _view(self.ptr, nbytes, np.uint8)
+
+    def view(self, dtype, offset, count):
+        item = np.dtype(dtype).itemsize
+        return self.buffer[offset: offset + count * item].view(dtype)
+
+    def free(self):
+        if self.ptr:
+            self.buffer = None
+            self._lib.wfb_host_free(self.ptr)
+            self.ptr = None
+
+
+class ModuleExports:
+    """Looks like `instance.exports` of a reference module: ONE `memory` laid out like the WAT
+    memory map, `precompute_*` that (re)targets the instance at a size -- calling it with a new n silently re-targets,
+    tests/boundary.test.js:304-332 -- and SYNCHRONOUS transform calls that work in place on that memory.  The memory is
+    pinned and device-mapped, so a call is one kernel reading and writing those very bytes (no copies), returning when
+    the results are in `memory`: a test may read them on the next line, as the reference suites do
+    (tests/fft_split_native.test.js:78-114).
+
+      fft_split_native_f32 : REAL_OFFSET, IMAG_OFFSET, precompute_twiddles_split, precompute_rfft_twiddles_split,
+                             fft_split, ifft_split, rfft_split, irfft_split
+      fft_stockham_f32_dual: precompute_twiddles, fft, ifft
+      fft_combined         : precompute_twiddles, fft, ifft
+      fft_real_combined    : precompute_rfft_twiddles, rfft   (+ irfft: extension, the reference export is missing)
+      fft_real_f32_dual    : precompute_rfft_twiddles, rfft, irfft
+    """
+
+    PAGES = {"fft_split_native_f32": 8, "fft_stockham_f32_dual": 4, "fft_combined": 6, "fft_real_combined": 8,
+             "fft_real_f32_dual": 6}
+    REAL_OFFSET = 0
+    IMAG_OFFSET = 32768
+
+    def __init__(self, module="fft_split_native_f32", device=0):
+        if module not in self.PAGES:
+            raise ValueError(module)
+        lib = C.lib()
+        rc = lib.wfb_require_b200(device)
+        if rc:
+            raise C.WatFFTError(rc)
+        self.module, self.device = module, device
+        self.memory = HostMemory(self.PAGES[module] * 65536)
+        self._plans = {}
+        self._f64 = module in ("fft_combined", "fft_real_combined")
+
+    # -- plan cache: (kind, layout, n) -> Plan without buffers of its own (it runs on `memory`)
+    def _plan(self, kind, layout, n):
+        key = (kind, layout, n)
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = Plan(kind, C.F64 if self._f64 else C.F32, layout, n, 1, self.device, C.PLAN_NO_HOST_BUFFERS)
+        return p
+
+    def _mem(self, dtype, offset, count):
+        return self.memory.view(dtype, offset, count)
+
+    def _run(self, plan, direction, off0, off1=None):
+        base = self.memory.ptr
+        planes = (base + off0, base + off1 if off1 is not None else None)
+        plan.exec_host(direction, planes, planes)          # in place, synchronous
+        return plan
+
+    # split module
+    def precompute_twiddles_split(self, n):
+        self._plan(C.C2C, C.SPLIT, n)
+
+    def precompute_rfft_twiddles_split(self, n):
+        self._plan(C.R2C, C.INTERLEAVED, n)
+
+    def fft_split(self, n):
+        self._run(self._plan(C.C2C, C.SPLIT, n), C.FORWARD, self.REAL_OFFSET, self.IMAG_OFFSET)
+
+    def ifft_split(self, n):
+        self._run(self._plan(C.C2C, C.SPLIT, n), C.INVERSE, self.REAL_OFFSET, self.IMAG_OFFSET)
+
+    def rfft_split(self, n):
+        self._run(self._plan(C.R2C, C.INTERLEAVED, n), C.FORWARD, 0)
+
+    def irfft_split(self, n):
+        self._run(self._plan(C.R2C, C.INTERLEAVED, n), C.INVERSE, 0)
+
+    # interleaved complex modules
+    def precompute_twiddles(self, n):
+        self._plan(C.C2C, C.INTERLEAVED, n)
+
+    def fft(self, n):
+        self._run(self._plan(C.C2C, C.INTERLEAVED, n), C.FORWARD, 0)
+
+    def ifft(self, n):
+        self._run(self._plan(C.C2C, C.INTERLEAVED, n), C.INVERSE, 0)
+
+    # real modules (f64: fft_real_combined, f32: fft_real_f32_dual)
+    def precompute_rfft_twiddles(self, n):
+        self._plan(C.R2C, C.INTERLEAVED, n)
+
+    def rfft(self, n):
+        self._run(self._plan(C.R2C, C.INTERLEAVED, n), C.FORWARD, 0)
+
+    def irfft(self, n):          # f64: extension (the reference module has no such export, index.js:145-147)
+        self._run(self._plan(C.R2C, C.INTERLEAVED, n), C.INVERSE, 0)
+
+    def dispose(self):
+        for p in self._plans.values():
+            p.destroy()
+        self._plans.clear()
+        if self.memory is not None:
+            self.memory.free()
+            self.memory = None
+
+
+SplitExportsFacade = ModuleExports          # (round-1 name)
+
+
+# ---- low-level instance factories (index.js:28-58; async there, synchronous here) -----------
+def createFFTInstance(device=0):
+    """raw instance for complex FFT (f64): memory, precompute_twiddles, fft, ifft (index.js:28-31)"""
+    return ModuleExports("fft_combined", device)
+
+
+def createFFTf32Instance(device=0):
+    """raw instance for complex FFT (f32, interleaved) (index.js:37-40)"""
+    return ModuleExports("fft_stockham_f32_dual", device)
+
+
+def createRFFTInstance(device=0):
+    """raw instance for real FFT (f64) (index.js:46-49)"""
+    return ModuleExports("fft_real_combined", device)
+
+
+def createRFFTf32Instance(device=0):
+    """raw instance for real FFT (f32) (index.js:55-58)"""
+    return ModuleExports("fft_real_f32_dual", device)
+
+
+def createFFTf32SplitInstance(device=0):
+    """raw instance of the split-format module (the reference exposes it only to its tests and benchmarks)"""
+    return ModuleExports("fft_split_native_f32", device)
+
+
+class _Context:
+    """Shared shape: {size, batch, exports, plan, forward, inverse, dispose}.
+    batch = 1: `exports` is the instance the context runs on (the reference's construction, index.js:69-91).
+    batch > 1: the context owns a plan with batch-sized pinned buffers; `exports` is a module instance of its own,
+    created on first use (its `memory` is one transform wide, so it cannot be the batch buffers)."""
+
+    _module = None
+
+    def _init(self, size, batch, device):
+        self.size, self.batch, self._device = size, batch, device
+        self._exports = ModuleExports(self._module, device) if batch == 1 else None
+        self._disposed = False
+
+    @property
+    def exports(self):
+        self._check()
+        if self._exports is None:
+            self._exports = ModuleExports(self._module, self._device)
+        return self._exports
+
+    def _check(self):
+        if self._disposed:
+            raise RuntimeError("watfft_b200: context used after dispose()")
+
+    def dispose(self):                      # idempotent
+        if self._disposed:
+            return
+        self._disposed = True
+        self._drop_views()
+        if self._exports is not None:
+            self._exports.dispose()
+        if self.batch > 1 and self.plan is not None:
+            self.plan.destroy()
+        self.plan = None
+
+
+class _ComplexContext(_Context):
+    """createFFT / createFFTf32 shape: {size, exports, getInputBuffer, getOutputBuffer, forward, inverse}."""
 
     def __init__(self, size, precision, batch, device):
-        self.size, self.batch = size, batch
-        self.plan = Plan(C.C2C, precision, C.INTERLEAVED, size, batch, device)
-        self._buf = self.plan.host(0)           # batch * 2 * size values
+        self._module = "fft_combined" if precision == C.F64 else "fft_stockham_f32_dual"
+        dtype = np.float64 if precision == C.F64 else np.float32
+        lo, hi = ctypes.c_int(), ctypes.c_int()
+        C.check(C.lib().wfb_size_range(C.C2C, precision, C.INTERLEAVED, lo, hi))
+        if size < lo.value or size > hi.value or size & (size - 1):
+            raise C.WatFFTError(C.ERR_BAD_SIZE)
+        self._init(size, batch, device)
+        if batch == 1:
+            ex = self._exports
+            ex.precompute_twiddles(size)
+            self.plan = ex._plan(C.C2C, C.INTERLEAVED, size)
+            self._buf = ex.memory.view(dtype, 0, 2 * size)
+            self._fwd, self._inv = (lambda: ex.fft(size)), (lambda: ex.ifft(size))
+        else:
+            self.plan = Plan(C.C2C, precision, C.INTERLEAVED, size, batch, device)
+            self._buf = self.plan.host(0)           # batch * 2 * size values
+            self._fwd, self._inv = (lambda: self.plan.exec(C.FORWARD)), (lambda: self.plan.exec(C.INVERSE))
 
     def getInputBuffer(self):
+        self._check()
         return self._buf
 
     def getOutputBuffer(self):                  # same bytes: in-place contract (index.js:78-83)
+        self._check()
         return self._buf
 
     def forward(self):
-        self.plan.exec(C.FORWARD)
+        self._check()
+        self._fwd()
 
     def inverse(self):
-        self.plan.exec(C.INVERSE)
+        self._check()
+        self._inv()
 
-    def dispose(self):
+    def _drop_views(self):
         self._buf = None
-        self.plan.destroy()
 
 
-class _SplitContext:
+class _SplitContext(_Context):
     """Split-format f32 context (the reference exposes this only as raw exports)."""
 
+    _module = "fft_split_native_f32"
+
     def __init__(self, size, batch, device):
-        self.size, self.batch = size, batch
-        self.plan = Plan(C.C2C, C.F32, C.SPLIT, size, batch, device)
-        self._re, self._im = self.plan.host(0), self.plan.host(1)
+        if size < 4 or size > 8192 or size & (size - 1):
+            raise C.WatFFTError(C.ERR_BAD_SIZE)
+        self._init(size, batch, device)
+        if batch == 1:
+            ex = self._exports
+            ex.precompute_twiddles_split(size)
+            self.plan = ex._plan(C.C2C, C.SPLIT, size)
+            self._re = ex.memory.view(np.float32, ex.REAL_OFFSET, size)
+            self._im = ex.memory.view(np.float32, ex.IMAG_OFFSET, size)
+            self._fwd, self._inv = (lambda: ex.fft_split(size)), (lambda: ex.ifft_split(size))
+        else:
+            self.plan = Plan(C.C2C, C.F32, C.SPLIT, size, batch, device)
+            self._re, self._im = self.plan.host(0), self.plan.host(1)
+            self._fwd, self._inv = (lambda: self.plan.exec(C.FORWARD)), (lambda: self.plan.exec(C.INVERSE))
 
     def getRealBuffer(self):
+        self._check()
         return self._re
 
     def getImagBuffer(self):
+        self._check()
         return self._im
 
     def getInputBuffer(self):
+        self._check()
         return self._re, self._im
 
     def getOutputBuffer(self):
+        self._check()
         return self._re, self._im
 
     def forward(self):
-        self.plan.exec(C.FORWARD)
+        self._check()
+        self._fwd()
 
     def inverse(self):
-        self.plan.exec(C.INVERSE)
+        self._check()
+        self._inv()
 
-    def dispose(self):
+    def _drop_views(self):
         self._re = self._im = None
-        self.plan.destroy()
 
 
-class _RealContext:
+class _RealContext(_Context):
     """createRFFT / createRFFTf32 shape: input = size reals, output = (size/2+1)*2 values.
 
     forward() reads getInputBuffer() and writes getOutputBuffer(); inverse() reads
@@ -166,30 +398,41 @@ class _RealContext:
     at the same address, exactly like the reference's views over memory offset 0."""
 
     def __init__(self, size, precision, batch, device):
-        self.size, self.batch = size, batch
-        self.plan = Plan(C.R2C, precision, C.INTERLEAVED, size, batch, device)
-        spec = self.plan.host(C.BUF_SPECTRUM)
+        self._module = "fft_real_combined" if precision == C.F64 else "fft_real_f32_dual"
+        dtype = np.float64 if precision == C.F64 else np.float32
+        if size < 8 or size > 16384 or size & (size - 1):
+            raise C.WatFFTError(C.ERR_BAD_SIZE)
+        self._init(size, batch, device)
         if batch == 1:
-            self._time = spec[:size]
+            ex = self._exports
+            ex.precompute_rfft_twiddles(size)
+            self.plan = ex._plan(C.R2C, C.INTERLEAVED, size)
+            self._time = ex.memory.view(dtype, 0, size)
+            self._spec = ex.memory.view(dtype, 0, size + 2)
+            self._fwd, self._inv = (lambda: ex.rfft(size)), (lambda: ex.irfft(size))
         else:
-            self._time = self.plan.host(C.BUF_TIME)
-        self._spec = spec
+            self.plan = Plan(C.R2C, precision, C.INTERLEAVED, size, batch, device)
+            self._time, self._spec = self.plan.host(C.BUF_TIME), self.plan.host(C.BUF_SPECTRUM)
+            self._fwd, self._inv = (lambda: self.plan.exec(C.FORWARD)), (lambda: self.plan.exec(C.INVERSE))
 
     def getInputBuffer(self):
+        self._check()
         return self._time
 
     def getOutputBuffer(self):
+        self._check()
         return self._spec
 
     def forward(self):
-        self.plan.exec(C.FORWARD)
+        self._check()
+        self._fwd()
 
     def inverse(self):
-        self.plan.exec(C.INVERSE)
+        self._check()
+        self._inv()
 
-    def dispose(self):
+    def _drop_views(self):
         self._time = self._spec = None
-        self.plan.destroy()
 
 
 # ---- factories: same names as index.js (async there, synchronous here) -------------------
@@ -220,112 +463,3 @@ def createFFTf32Split(size, batch=1, device=0):
 
 
 createRFFTf32Split = createRFFTf32
-
-
-# ---- exports-shaped facade ------------------------------------------------------------------
-class SplitExportsFacade:
-    """Looks like `instance.exports` of a reference module so the reference's own suites (which
-    poke raw exports) can be pointed at the GPU: a host `memory` laid out like
-    the WAT memory map, precompute_* that (re)targets the instance at a size, and transform calls
-    that stage memory -> GPU -> memory.  One facade per module name:
-
-      fft_split_native_f32 : REAL_OFFSET, IMAG_OFFSET, precompute_twiddles_split,
-                             precompute_rfft_twiddles_split, fft_split, ifft_split, rfft_split, irfft_split
-      fft_stockham_f32_dual: precompute_twiddles, fft, ifft
-      fft_combined         : precompute_twiddles, fft, ifft
-      fft_real_combined    : precompute_rfft_twiddles, rfft   (+ irfft extension)
-    """
-
-    PAGES = {"fft_split_native_f32": 8, "fft_stockham_f32_dual": 4, "fft_combined": 6, "fft_real_combined": 8}
-    REAL_OFFSET = 0
-    IMAG_OFFSET = 32768
-
-    def __init__(self, module="fft_split_native_f32", device=0):
-        if module not in self.PAGES:
-            raise ValueError(module)
-        self.module, self.device = module, device
-        self.memory = np.zeros(self.PAGES[module] * 65536, np.uint8)
-        self._plans = {}
-
-    def _plan(self, kind, precision, layout, n):
-        key = (kind, precision, layout, n)
-        if key not in self._plans:
-            self._plans[key] = Plan(kind, precision, layout, n, 1, self.device)
-        return self._plans[key]
-
-    def _mem(self, dtype, offset, count):
-        item = np.dtype(dtype).itemsize
-        return self.memory[offset: offset + count * item].view(dtype)
-
-    # split module
-    def precompute_twiddles_split(self, n):
-        self._plan(C.C2C, C.F32, C.SPLIT, n)
-
-    def precompute_rfft_twiddles_split(self, n):
-        self._plan(C.R2C, C.F32, C.INTERLEAVED, n)
-
-    def _c2c_split(self, n, direction):
-        p = self._plan(C.C2C, C.F32, C.SPLIT, n)
-        p.host(0)[:] = self._mem(np.float32, self.REAL_OFFSET, n)
-        p.host(1)[:] = self._mem(np.float32, self.IMAG_OFFSET, n)
-        p.exec(direction)
-        self._mem(np.float32, self.REAL_OFFSET, n)[:] = p.host(0)
-        self._mem(np.float32, self.IMAG_OFFSET, n)[:] = p.host(1)
-
-    def fft_split(self, n):
-        self._c2c_split(n, C.FORWARD)
-
-    def ifft_split(self, n):
-        self._c2c_split(n, C.INVERSE)
-
-    def _real(self, n, precision, direction):
-        p = self._plan(C.R2C, precision, C.INTERLEAVED, n)
-        dt = p.dtype
-        spec = p.host(C.BUF_SPECTRUM)
-        if direction == C.FORWARD:
-            spec[:n] = self._mem(dt, 0, n)
-            p.exec(C.FORWARD)
-            self._mem(dt, 0, n + 2)[:] = spec
-        else:
-            spec[:] = self._mem(dt, 0, n + 2)
-            p.exec(C.INVERSE)
-            self._mem(dt, 0, n)[:] = spec[:n]
-
-    def rfft_split(self, n):
-        self._real(n, C.F32, C.FORWARD)
-
-    def irfft_split(self, n):
-        self._real(n, C.F32, C.INVERSE)
-
-    # interleaved modules
-    def precompute_twiddles(self, n):
-        prec = C.F64 if self.module == "fft_combined" else C.F32
-        self._plan(C.C2C, prec, C.INTERLEAVED, n)
-
-    def _c2c_il(self, n, direction):
-        prec = C.F64 if self.module == "fft_combined" else C.F32
-        p = self._plan(C.C2C, prec, C.INTERLEAVED, n)
-        p.host(0)[:] = self._mem(p.dtype, 0, 2 * n)
-        p.exec(direction)
-        self._mem(p.dtype, 0, 2 * n)[:] = p.host(0)
-
-    def fft(self, n):
-        self._c2c_il(n, C.FORWARD)
-
-    def ifft(self, n):
-        self._c2c_il(n, C.INVERSE)
-
-    # f64 real module
-    def precompute_rfft_twiddles(self, n):
-        self._plan(C.R2C, C.F64, C.INTERLEAVED, n)
-
-    def rfft(self, n):
-        self._real(n, C.F64, C.FORWARD)
-
-    def irfft(self, n):          # extension (the reference module has no such export)
-        self._real(n, C.F64, C.INVERSE)
-
-    def dispose(self):
-        for p in self._plans.values():
-            p.destroy()
-        self._plans.clear()

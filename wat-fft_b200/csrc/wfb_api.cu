@@ -132,6 +132,44 @@ cudaError_t launch_persistent_raw(const void *kernel, size_t smem, int threads, 
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// persistent launch with per-call dynamic shared memory (k_stft_span): the opt-in limit is raised once per kernel, the
+// resident-CTA count is cached per (device, kernel, bytes)
+cudaError_t launch_persistent_dyn(const void *kernel, size_t smem, int threads, long work_items, const StftParams &sp0, cudaStream_t s) {
+    if (!kernel) return cudaErrorInvalidDeviceFunction;
+    static std::map<std::pair<std::pair<int, const void *>, size_t>, int> cache;
+    static std::set<std::pair<int, const void *>> raised;
+    int dev = 0, resident = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        const auto fk = std::make_pair(dev, kernel);
+        if (!raised.count(fk)) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            raised.insert(fk);
+        }
+        const auto key = std::make_pair(fk, smem);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            int per_sm = 0, sms = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+            if (e != cudaSuccess) return e;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (per_sm < 1) return cudaErrorInvalidConfiguration;
+            it = cache.emplace(key, per_sm * sms).first;
+        }
+        resident = it->second;
+    }
+    StftParams sp = sp0;
+    cudaError_t e = next_counter(s, &sp.ctr);
+    if (e != cudaSuccess) return e;
+    long grid = work_items < resident ? work_items : resident;
+    void *args[] = {&sp};
+    e = cudaLaunchKernel(kernel, dim3((unsigned)grid), dim3(threads), args, smem, s);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 // persistent kernels: grid = min(work items, CTAs resident on the whole GPU)
 cudaError_t launch_persistent(const void *kernel, size_t smem, int threads, long work_items, const KParams &p, cudaStream_t s) {
     if (!kernel) return cudaErrorInvalidDeviceFunction;
@@ -154,7 +192,7 @@ cudaError_t launch_persistent(const void *kernel, size_t smem, int threads, long
 // memory per GPU) with per-size free lists; only allocations above SMALL_MAX go to the driver directly.
 // ----------------------------------------------------------------------------------------
 struct SmallPool {
-    enum : size_t { SLAB = 4u << 20, SMALL_MAX = 256u << 10 };
+    enum : size_t { SLAB = 4u << 20, SMALL_MAX = 512u << 10 };      // (a module-sized host arena is 4-8 WASM pages = 256-512 KiB)
     bool host;
     int device;
     char *cur = nullptr;
@@ -490,22 +528,23 @@ static int plan_init(wfb_plan *pl) {
         }
         for (int i = 0; i < 2; i++)
             if (pl->h_buf[i] && cudaHostGetDevicePointer(&pl->hd_buf[i], pl->h_buf[i], 0) != cudaSuccess) { cudaGetLastError(); pl->hd_buf[0] = pl->hd_buf[1] = nullptr; break; }
-        // completion flag (host word) + CTA counter (device word) of the zero-copy path
-        void *f = nullptr, *c = nullptr;
-        if (pl->hd_buf[0] && host_alloc(256, &f) == cudaSuccess && dev_alloc(pl->device, 256, &c) == cudaSuccess) {
-            pl->h_flag = (volatile unsigned *)f;
-            *pl->h_flag = 0;
-            pl->d_done_ctr = (unsigned *)c;
-            if (cudaHostGetDevicePointer((void **)&pl->hd_flag, f, 0) != cudaSuccess ||
-                cudaMemsetAsync(c, 0, 256, pl->stream) != cudaSuccess || cudaStreamSynchronize(pl->stream) != cudaSuccess) {
-                cudaGetLastError();
-                pl->hd_flag = nullptr;
-            }
-        } else {
+    }
+    // completion flag (host word) + CTA counter (device word) of the zero-copy path (also used by wfb_exec_host on
+    // plans without host buffers of their own)
+    void *f = nullptr, *c = nullptr;
+    if (host_alloc(256, &f) == cudaSuccess && dev_alloc(pl->device, 256, &c) == cudaSuccess) {
+        pl->h_flag = (volatile unsigned *)f;
+        *pl->h_flag = 0;
+        pl->d_done_ctr = (unsigned *)c;
+        if (cudaHostGetDevicePointer((void **)&pl->hd_flag, f, 0) != cudaSuccess ||
+            cudaMemsetAsync(c, 0, 256, pl->stream) != cudaSuccess || cudaStreamSynchronize(pl->stream) != cudaSuccess) {
             cudaGetLastError();
-            if (f) host_free(f, 256);
-            if (c) dev_free(pl->device, c, 256);
+            pl->hd_flag = nullptr;
         }
+    } else {
+        cudaGetLastError();
+        if (f) host_free(f, 256);
+        if (c) dev_free(pl->device, c, 256);
     }
     int rc;
     if (use_mapped(pl)) {
@@ -702,10 +741,27 @@ int wfb_sync(wfb_plan *pl) {
     return WFB_OK;
 }
 
-int wfb_exec(wfb_plan *pl, int direction, int flags) {
-    if (!pl || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
+}  // extern "C"
+
+// Host arenas handed out by wfb_host_alloc: base -> (bytes, device-side address).  wfb_exec_host accepts only pointers
+// inside one of them (pinned + device-mapped memory is what both of its paths need).
+struct Arena { size_t bytes; char *dev; };
+static std::map<uintptr_t, Arena> g_arenas;
+static bool arena_lookup(const void *p, size_t need, void **dev_alias) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_arenas.upper_bound((uintptr_t)p);
+    if (it == g_arenas.begin()) return false;
+    --it;
+    const uintptr_t off = (uintptr_t)p - it->first;
+    if (off + need > it->second.bytes) return false;
+    *dev_alias = it->second.dev + off;
+    return true;
+}
+
+// wfb_exec / wfb_exec_host: `hs`, `hd` = host addresses of the planes read and written (indexed like src[] / dst[] below),
+// `as`, `ad` = the device-side addresses of the same bytes (zero-copy path; null when the memory is not mapped)
+static int exec_impl(wfb_plan *pl, int direction, int flags, void *const hs_in[2], void *const hd_in[2], void *const as_in[2], void *const ad_in[2]) {
     if (pl->flags & WFB_PLAN_NO_DEVICE_BUFFERS) return WFB_ERR_BAD_ARG;
-    if ((flags & (WFB_STAGE_H2D | WFB_STAGE_D2H)) && !pl->h_buf[0] && !pl->h_buf[1]) return WFB_ERR_NO_HOST_BUFFERS;
     CK(cudaSetDevice(pl->device));
     // buffer ids and per-row byte strides of the planes read and written
     int src[2] = {-1, -1}, dst[2] = {-1, -1};
@@ -721,17 +777,23 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
         src_row[0] = e * (a == WFB_BUF_TIME ? n : n + 2);
         dst_row[0] = e * (a == WFB_BUF_TIME ? n + 2 : n);
     }
+    // host / alias pointers per plane slot: the plan's own buffers unless the caller supplied some
+    void *hs[2] = {nullptr, nullptr}, *hd[2] = {nullptr, nullptr}, *as[2] = {nullptr, nullptr}, *ad[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) {
+        if (src[i] >= 0) { hs[i] = hs_in ? hs_in[i] : pl->h_buf[src[i]]; as[i] = hs_in ? as_in[i] : pl->hd_buf[src[i]]; }
+        if (dst[i] >= 0) { hd[i] = hd_in ? hd_in[i] : pl->h_buf[dst[i]]; ad[i] = hd_in ? ad_in[i] : pl->hd_buf[dst[i]]; }
+    }
     const bool h2d = flags & WFB_STAGE_H2D, d2h = flags & WFB_STAGE_D2H;
 
     // ---- zero-copy path (small payloads; the reference's own call shape is batch = 1, index.js:84-89): ONE launch of
     // the direct-load kernel on the mapped host buffers -- the loads and stores cross PCIe themselves, so there is no
     // copy node in front of or behind the kernel and nothing to wait for but the kernel.  In place is safe: every CTA of
     // the direct kernels has all its rows in registers (behind a barrier for multi-pass plans) before its first store.
-    if (h2d && d2h && use_mapped(pl)) {
+    const bool mapped_ok = as[0] && ad[0] && pl->mapped_variant >= 0 && (long)payload_bytes(pl) <= pl->mapped_max_bytes;
+    if (h2d && d2h && mapped_ok) {
         const bool flagged = (flags & WFB_SYNC) && pl->hd_flag;
         if (flagged) pl->token++;
-        int rc = launch_rows(pl, direction, pl->hd_buf[src[0]], src[1] >= 0 ? pl->hd_buf[src[1]] : nullptr,
-                             pl->hd_buf[dst[0]], dst[1] >= 0 ? pl->hd_buf[dst[1]] : nullptr, pl->batch, pl->stream, pl->mapped_variant, flagged);
+        int rc = launch_rows(pl, direction, as[0], as[1], ad[0], ad[1], pl->batch, pl->stream, pl->mapped_variant, flagged);
         if (rc) return rc;
         pl->last_path = WFB_PATH_MAPPED;
         if (flagged) {
@@ -767,13 +829,13 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
         pl->last_path = WFB_PATH_STAGED;
         if (h2d)
             for (int i = 0; i < 2; i++)
-                if (src[i] >= 0) CK(cudaMemcpyAsync(pl->d_buf[src[i]], pl->h_buf[src[i]], pl->bytes[src[i]], cudaMemcpyHostToDevice, pl->stream));
+                if (src[i] >= 0) CK(cudaMemcpyAsync(pl->d_buf[src[i]], hs[i], pl->bytes[src[i]], cudaMemcpyHostToDevice, pl->stream));
         int rc = launch_rows(pl, direction, pl->d_buf[src[0]], src[1] >= 0 ? pl->d_buf[src[1]] : nullptr,
                              pl->d_buf[dst[0]], dst[1] >= 0 ? pl->d_buf[dst[1]] : nullptr, pl->batch, pl->stream);
         if (rc) return rc;
         if (d2h)
             for (int i = 0; i < 2; i++)
-                if (dst[i] >= 0) CK(cudaMemcpyAsync(pl->h_buf[dst[i]], pl->d_buf[dst[i]], pl->bytes[dst[i]], cudaMemcpyDeviceToHost, pl->stream));
+                if (dst[i] >= 0) CK(cudaMemcpyAsync(hd[i], pl->d_buf[dst[i]], pl->bytes[dst[i]], cudaMemcpyDeviceToHost, pl->stream));
     } else {
         pl->last_path = WFB_PATH_PIPELINED;
         if (int rc = ensure_pipeline(pl)) return rc;
@@ -790,7 +852,7 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
             for (int i = 0; i < 2; i++) {
                 if (src[i] >= 0) {
                     di[i] = (char *)pl->d_buf[src[i]] + (size_t)r0 * src_row[i];
-                    if (h2d) CK(cudaMemcpyAsync(di[i], (char *)pl->h_buf[src[i]] + (size_t)r0 * src_row[i], (size_t)rows * src_row[i], cudaMemcpyHostToDevice, s));
+                    if (h2d) CK(cudaMemcpyAsync(di[i], (char *)hs[i] + (size_t)r0 * src_row[i], (size_t)rows * src_row[i], cudaMemcpyHostToDevice, s));
                 }
                 if (dst[i] >= 0) dout[i] = (char *)pl->d_buf[dst[i]] + (size_t)r0 * dst_row[i];
             }
@@ -798,7 +860,7 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
             if (rc) return rc;
             if (d2h)
                 for (int i = 0; i < 2; i++)
-                    if (dst[i] >= 0) CK(cudaMemcpyAsync((char *)pl->h_buf[dst[i]] + (size_t)r0 * dst_row[i], dout[i], (size_t)rows * dst_row[i], cudaMemcpyDeviceToHost, s));
+                    if (dst[i] >= 0) CK(cudaMemcpyAsync((char *)hd[i] + (size_t)r0 * dst_row[i], dout[i], (size_t)rows * dst_row[i], cudaMemcpyDeviceToHost, s));
         }
         for (int i = 0; i < nstreams; i++) {
             CK(cudaEventRecord(pl->pipe_done[i], pl->pipe[i]));
@@ -808,6 +870,62 @@ int wfb_exec(wfb_plan *pl, int direction, int flags) {
     if (flags & WFB_SYNC) CK(cudaStreamSynchronize(pl->stream));
     return WFB_OK;
 }
+
+extern "C" {
+
+int wfb_exec(wfb_plan *pl, int direction, int flags) {
+    if (!pl || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
+    if ((flags & (WFB_STAGE_H2D | WFB_STAGE_D2H)) && !pl->h_buf[0] && !pl->h_buf[1]) return WFB_ERR_NO_HOST_BUFFERS;
+    return exec_impl(pl, direction, flags, nullptr, nullptr, nullptr, nullptr);
+}
+
+void *wfb_host_alloc(size_t bytes) {
+    if (bytes == 0) return nullptr;
+    void *p = nullptr, *d = nullptr;
+    if (host_alloc(bytes, &p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    memset(p, 0, bytes);
+    if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); host_free(p, bytes); return nullptr; }
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_arenas[(uintptr_t)p] = Arena{bytes, (char *)d};
+    return p;
+}
+
+void wfb_host_free(void *p) {
+    if (!p) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_arenas.find((uintptr_t)p);
+        if (it == g_arenas.end()) return;
+        bytes = it->second.bytes;
+        g_arenas.erase(it);
+    }
+    host_free(p, bytes);
+}
+
+int wfb_exec_host(wfb_plan *pl, int direction, const void *const h_in[2], void *const h_out[2], int flags) {
+    if (!pl || !h_in || !h_out || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
+    const bool two = pl->kind == WFB_C2C && pl->layout == WFB_SPLIT;
+    size_t in_bytes[2], out_bytes[2];
+    if (pl->kind == WFB_C2C) { in_bytes[0] = out_bytes[0] = pl->bytes[0]; in_bytes[1] = out_bytes[1] = pl->bytes[1]; }
+    else {
+        const int a = direction == WFB_FORWARD ? WFB_BUF_TIME : WFB_BUF_SPECTRUM;
+        in_bytes[0] = pl->bytes[a]; out_bytes[0] = pl->bytes[1 - a]; in_bytes[1] = out_bytes[1] = 0;
+    }
+    void *hs[2] = {nullptr, nullptr}, *hd[2] = {nullptr, nullptr}, *as[2] = {nullptr, nullptr}, *ad[2] = {nullptr, nullptr};
+    for (int i = 0; i < (two ? 2 : 1); i++) {
+        if (!h_in[i] || !h_out[i]) return WFB_ERR_BAD_ARG;
+        if (!arena_lookup(h_in[i], in_bytes[i], &as[i]) || !arena_lookup(h_out[i], out_bytes[i], &ad[i])) return WFB_ERR_BAD_ARG;
+        hs[i] = const_cast<void *>(h_in[i]); hd[i] = h_out[i];
+    }
+    // in place needs rows of equal stride on both sides (C2C always; R2C only at batch = 1, where a row is the whole buffer)
+    if (pl->kind == WFB_R2C && pl->batch > 1 && h_in[0] == h_out[0]) return WFB_ERR_BAD_ARG;
+    return exec_impl(pl, direction, flags | WFB_STAGE_H2D | WFB_STAGE_D2H, hs, hd, as, ad);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // Pinned-copy ceiling of the link wfb_exec stages over: plain cudaMemcpyAsync between a pinned host buffer and the
 // device, each direction alone and both at once (one stream each), CUDA-event timed.  bench.py runs it on every rank
@@ -982,6 +1100,7 @@ int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void
     sp.frames = st->frames; sp.hop = st->hop; sp.wsize = st->wsize; sp.mode = st->mode & 0xFF;
     sp.db_floor = st->db_floor; sp.inv_range = st->inv_range; sp.inv_half_n = 2.0f / (float)st->fft_size;
     sp.ctr = nullptr;
+    sp.span_bytes = 0;
     sp.aligned8 = ((uintptr_t)d_samples % 8) == 0;      // a caller's pointer may be any float address (scalar loads then)
     // fast dB path: v = lg_a * log2(|2 X|^2) + lg_b  ==  (10 log10(|X|^2 c^2) - floor) / range,  c = 2 / fft_size
     sp.lg_a = 3.0102999566398120f * st->inv_range;
@@ -989,7 +1108,15 @@ int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void
     // frames are TMA-copyable when their starts are 16-byte aligned (hop % 4 == 0, aligned base)
     static const int pipe_min = [] { const char *e = getenv("WFB_STFT_PIPE_MIN_N"); return e ? atoi(e) : 8192; }();
     const bool pipe = st->fft_size >= pipe_min && st->hop % 4 == 0 && st->wsize % 4 == 0 && ((uintptr_t)d_samples % 16) == 0;
-    cudaError_t e = (pipe ? st->variant->launch_pipe : st->variant->launch)(sp, stream ? (cudaStream_t)stream : st->stream);
+    cudaStream_t cs = stream ? (cudaStream_t)stream : st->stream;
+    // span kernel: whole tiles of overlapping frames as one bulk copy (16-byte aligned frame starts and sizes)
+    const char *span_env = getenv("WFB_STFT_SPAN");             // (read per call: tests and A/B runs flip it)
+    const bool span_on = !span_env || atoi(span_env) != 0;
+    cudaError_t e = cudaErrorInvalidConfiguration;
+    if (span_on && st->variant->launch_span && st->hop % 4 == 0 && st->wsize % 4 == 0 && ((uintptr_t)d_samples % 16) == 0 &&
+        ((uintptr_t)d_out % 16) == 0)
+        e = st->variant->launch_span(sp, cs);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = (pipe ? st->variant->launch_pipe : st->variant->launch)(sp, cs); }
     if (e != cudaSuccess) return cuda_fail(e, "stft launch");
     return WFB_OK;
 }

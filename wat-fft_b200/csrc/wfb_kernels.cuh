@@ -1904,6 +1904,7 @@ struct StftParams {
     unsigned long long *ctr;   // pipelined kernel: zeroed tile counter of this launch
     float lg_a, lg_b;          // fast dB path: value = lg_a * log2(|2 X|^2) + lg_b (host-folded constants)
     int aligned8;              // `samples` is 8-byte aligned: even hops may use 64-bit loads
+    int span_bytes;            // span kernel: shared-memory bytes of one span stage (multiple of 128)
 };
 enum { STFT_MODE_DB = 0, STFT_MODE_COMPLEX = 1 };
 // kernel flavours (template parameter KM): the dB output has a fast path that needs no square root and folds every
@@ -2090,6 +2091,182 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(const __grid_const
         sync_transform<PL::T, X>(xi);
         if (active) stft_post<PL, LAST, KM>(x, scratch, rtw, tid, frame, sp);
     }
+    claim_epilogue(sp.ctr);
+}
+
+
+// ----------------------------------------------------------------------------------------
+// Span-staged persistent STFT (the default when hop and window are multiples of 4 samples).
+//   * The X frames of a tile overlap, so their samples are ONE contiguous span of (X-1)*hop + window floats: it arrives
+//     as ONE bulk copy (double-buffered, prefetched a tile ahead) and every frame is formed out of shared memory.  The
+//     direct kernel above re-loads every sample window/hop times through the L1 data pipe, its top-utilised unit.
+//   * The window function sits in shared memory for the whole kernel (the direct kernel re-loads it from global memory
+//     for every frame, through the tagged L1 path).
+//   * The dB (or complex) rows of a tile are contiguous in the output: they are assembled in shared memory and leave as
+//     one bulk store.  Rows are (M+1) floats, so a tile starts at any multiple of 4 bytes: the tile is assembled at the
+//     same 16-byte phase as its destination, the aligned interior goes out as a bulk store and the <= 3 floats at either
+//     end as plain stores.
+// Shared memory: [work: X padded scratch rows, reused for the result tile][span stage 0][span stage 1][mbarriers, slots][window].
+// ----------------------------------------------------------------------------------------
+template <class PL, int PADQ, int X> __host__ __device__ constexpr size_t stft_work_bytes() {
+    size_t a = sizeof(cx<float>) * (size_t)padded_size<PADQ>(PL::N) * X + 16;      // + the output phase offset
+    size_t b = sizeof(float) * 2 * (size_t)(PL::N + 1) * X + 16;                   // complex result tile
+    return ((a > b ? a : b) + 127) / 128 * 128;
+}
+
+// Hermitian post-process of one frame into REGISTER values: vk[i] = bin k = tid + i*T, vm[i] = bin M - k (thread 0:
+// vk[0] = bin 0, vm[0] = bin M, vh = bin M/2).  V is float (dB flavours) or float2 (complex).
+template <class PL, int LAST, int KM, typename V>
+__device__ __forceinline__ void stft_values(const cx<float> (&x)[PL::E], const cx<float> *park, const float2 *rtw, int tid,
+                                            const StftParams &sp, V (&vk)[PL::E / 2], V (&vm)[PL::E / 2], V &vh) {
+    using R = float;
+    constexpr int M = PL::N, HALF = M / 2, PER = PL::E / 2;
+    static_assert(PER * PL::T == HALF, "bins per thread");
+    auto conv = [&](int k, cx<R> v) -> V {                               // exact forms (and the three special bins)
+        if constexpr (KM == STFT_K_COMPLEX) return make_float2(v.x, v.y);
+        else return k < 3 ? 0.0f : stft_db(v.x, v.y, sp);               // DC and near-DC bins zeroed (:338-342)
+    };
+    static_for<PER>([&](auto I_) {
+        CIDX(i, I_);
+        const int k = tid + i * PL::T;
+        const cx<R> z = x[slot_of_elem<PL, LAST>(i)];                   // Z[k]: this thread's own output
+        if (i == 0 && k == 0) {
+            vk[0] = conv(0, mk<R>(z.x + z.y, 0.0f));
+            vm[0] = conv(M, mk<R>(z.x - z.y, 0.0f));
+            vh = conv(HALF, RealPost<R>::middle(park[HALF], ld_tw(rtw + HALF), M));
+        } else {
+            const cx<R> zm = park[k];
+            const twd<R> w = ld_tw(rtw + k);
+            if constexpr (KM == STFT_K_FAST) {
+                // 2 X[k] and 2 X[M-k]: RealPost::pair without its four multiplications by 1/2
+                const R gr = z.x + zm.x, gi = z.y - zm.y, hr = z.y + zm.y, hi = zm.x - z.x;
+                const R tr = fmaf(w.ny, hi, w.x * hr), ti = fmaf(w.y, hr, w.x * hi);
+                float a = stft_db_fast(mk<R>(gr + tr, gi + ti), sp);
+                if constexpr (i * PL::T < 3) a = k < 3 ? 0.0f : a;      // only the first block(s) hold bins below 3
+                vk[i] = a;
+                vm[i] = stft_db_fast(mk<R>(gr - tr, ti - gi), sp);
+            } else {
+                cx<R> xk, xm;
+                RealPost<R>::pair(z, zm, w, w, xk, xm);
+                vk[i] = conv(k, xk);
+                vm[i] = conv(M - k, xm);
+            }
+        }
+    });
+}
+
+template <class PL, int X, int PADQ, int MINB, int KM, bool PAD>
+__global__ void __launch_bounds__(PL::T *X, MINB) k_stft_span(const __grid_constant__ StftParams sp) {
+    static_assert(PL::valid() && PL::T * X >= 32, "needs a full issuing warp");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using R = float;
+    using V = typename std::conditional<KM == STFT_K_COMPLEX, float2, float>::type;
+    constexpr int M = PL::N, T = PL::T, E = PL::E, PER = E / 2, HALF = M / 2;
+    constexpr int LAST = PL::npass() - 1;
+    constexpr size_t WORK = stft_work_bytes<PL, PADQ, X>();
+    const uint32_t span_cap = (uint32_t)sp.span_bytes;                   // bytes per span stage (multiple of 128)
+    unsigned char *work = smem_raw;
+    unsigned char *span = smem_raw + WORK;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + WORK + 2 * (size_t)span_cap);
+    long *slot = reinterpret_cast<long *>(mbar + 4);
+    const int xi = threadIdx.x / T, tid = threadIdx.x % T;
+    const float2 *tw = reinterpret_cast<const float2 *>(sp.tw);
+    const float2 *rtw = reinterpret_cast<const float2 *>(sp.rtw);
+    const long tiles = (sp.frames + X - 1) / X;
+    constexpr int VW = (int)(sizeof(V) / sizeof(float));                 // floats per output bin
+    float *gout = reinterpret_cast<float *>(sp.out);
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar + 0, 1);
+        mbar_init(mbar + 1, 1);
+        fence_proxy_async();
+    }
+    // the window function, once per CTA, in shared memory behind the span stages (zero beyond the window): the frames are
+    // formed with two conflict-free LDS.64 per value pair.  (Holding each thread's window values in registers for the whole
+    // kernel was measured first: 64 more registers on the 32-value plans, 8 warps per SM, 8 % slower than the direct kernel.)
+    float2 *winsm = reinterpret_cast<float2 *>(smem_raw + WORK + 2 * (size_t)span_cap + 128);
+    {
+        const float2 *w2 = reinterpret_cast<const float2 *>(sp.window);
+        for (int pidx = threadIdx.x; pidx < M; pidx += T * X)
+            winsm[pidx] = (!PAD || 2 * pidx < sp.wsize) ? __ldg(w2 + pidx) : make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+
+    auto tile_rows = [&](long tile) { const long f0 = tile * X; return (sp.frames - f0 < X) ? (int)(sp.frames - f0) : X; };
+    auto issue = [&](long tile, int st) {
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)(((long)(tile_rows(tile) - 1) * sp.hop + sp.wsize) * sizeof(float));
+            mbar_expect_tx(mbar + st, bytes);
+            tma_load_1d(span + (size_t)st * span_cap, sp.samples + tile * X * (long)sp.hop, bytes, mbar + st);
+        }
+    };
+    // the result tile of `tile` sits in `work` at the 16-byte phase of its destination
+    auto out_phase = [&](long tile) { return (int)((tile * X * (long)(M + 1) * VW) & 3); };      // in floats
+    auto store_tile = [&](long tile) {
+        if (threadIdx.x >= 32) return;
+        const long o0 = tile * X * (long)(M + 1) * VW;                   // first float of the tile in the output
+        const int total = tile_rows(tile) * (M + 1) * VW, ph = out_phase(tile);
+        const int head = (4 - ph) & 3;                                   // floats up to the next 16-byte boundary
+        const int interior = (total - head) & ~3;
+        const float *src = reinterpret_cast<const float *>(work) + ph;
+        if (threadIdx.x == 0 && interior > 0) {
+            tma_store_1d(gout + o0 + head, src + head, (uint32_t)(interior * sizeof(float)));
+            bulk_commit();
+        }
+        if ((int)threadIdx.x < head) st_stream(gout + o0 + threadIdx.x, src[threadIdx.x]);
+        const int tail0 = head + interior;
+        if ((int)threadIdx.x < total - tail0) st_stream(gout + o0 + tail0 + threadIdx.x, src[tail0 + threadIdx.x]);
+    };
+
+    long pending = claim_prime<false>(sp.ctr);
+    claim_and_issue<false>(sp.ctr, pending, tiles, slot, 0, issue);
+    cx<R> x[E];
+    unsigned phasebits = 0;
+    long prev_tile = -1;
+    for (int it = 0;; it++) {
+        const int st = it & 1;
+        fence_proxy_async();       // the result tile written below (generic proxy) precedes its bulk store
+        __syncthreads();           // slot[st] is published; the result tile of the last iteration is complete
+        if (prev_tile >= 0) store_tile(prev_tile);
+        const long tile = slot[st];
+        if (tile >= tiles) break;
+        mbar_wait(mbar + st, (phasebits >> st) & 1u);
+        phasebits ^= 1u << st;
+        const long frame = tile * X + xi;
+        // hop is a multiple of 4 samples: every frame starts on a 16-byte boundary of the span
+        const float2 *raw = reinterpret_cast<const float2 *>(span + (size_t)st * span_cap) + (size_t)xi * (sp.hop >> 1);
+        static_for<E>([&](auto E_) {
+            CIDX(e, E_);
+            const int pidx = tid + e * T;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (!PAD || 2 * pidx < sp.wsize) v = raw[pidx];              // (frames past the last one read stale data and are dropped)
+            const float2 w = winsm[pidx];
+            x[e] = mk<R>(v.x * w.x, v.y * w.y);
+        });
+        if (threadIdx.x == 0) bulk_wait_read_all();                     // the last result tile has left `work` ...
+        __syncthreads();                                                 // ... before anyone uses it as scratch; all span reads done
+        claim_and_issue<false>(sp.ctr, pending, tiles, slot, st ^ 1, issue);   // (the other stage was consumed an iteration ago)
+        cx<R> *scratch = reinterpret_cast<cx<R> *>(work) + (size_t)xi * padded_size<PADQ>(M);
+        run_all<R, PL, PADQ, X, false>(x, tw, GTw<R>{nullptr, tw}, scratch, tid, xi, false);
+        if (PL::npass() > 1) sync_transform<T, X>(xi);
+        park_upper_half<R, PL, LAST>(x, scratch, tid);
+        sync_transform<T, X>(xi);
+        V vk[PER], vm[PER], vh = V();
+        stft_values<PL, LAST, KM, V>(x, scratch, rtw, tid, sp, vk, vm, vh);
+        __syncthreads();                                                 // every group has read its parked half: `work` becomes the result tile
+        if (frame < sp.frames) {
+            V *orow = reinterpret_cast<V *>(reinterpret_cast<float *>(work) + out_phase(tile)) + (size_t)xi * (M + 1);
+            static_for<PER>([&](auto I_) {
+                CIDX(i, I_);
+                const int k = tid + i * T;
+                orow[k] = vk[i];
+                orow[M - k] = vm[i];
+                if (i == 0 && k == 0) orow[HALF] = vh;
+            });
+        }
+        prev_tile = tile;
+    }
+    if (threadIdx.x == 0) bulk_wait_read_all();                         // shared memory must outlive the store that reads it
     claim_epilogue(sp.ctr);
 }
 

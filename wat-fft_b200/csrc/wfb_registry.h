@@ -179,7 +179,9 @@ template <class PL, int X, int MINB> struct RealTileLaunchers {
 
 // fused STFT (frame gather + window + r2c + magnitude/dB)
 typedef cudaError_t (*stft_launch_fn)(const StftParams &sp, cudaStream_t s);
-struct StftVariant { const char *name; int core_n; std::vector<int> radices; stft_launch_fn launch, launch_pipe; };
+struct StftVariant { const char *name; int core_n; std::vector<int> radices; stft_launch_fn launch, launch_pipe, launch_span; };
+// persistent launch whose dynamic shared memory varies from call to call (the span stages depend on hop and window)
+cudaError_t launch_persistent_dyn(const void *kernel, size_t smem, int threads, long work_items, const StftParams &sp, cudaStream_t s);
 cudaError_t launch_persistent_raw(const void *kernel, size_t smem, int threads, long work_items, void *params, cudaStream_t s);
 cudaError_t launch_grid_raw(const void *kernel, size_t smem, int threads, long ctas, void *params, cudaStream_t s);
 const std::vector<StftVariant> &variants_stft();
@@ -214,7 +216,32 @@ template <class PL, int X, int MINB, int PQ = PADQ> struct StftLaunchers {
         }
         return launch_persistent_raw(k, smem_pipe, PL::T * XP, (sp.frames + XP - 1) / XP, (void *)&sp, s);
     }
-    static StftVariant make(const char *name) { return StftVariant{name, PL::N, plan_radices<PL>(), &launch, &launch_pipe}; }
+    static StftVariant make(const char *name) { return StftVariant{name, PL::N, plan_radices<PL>(), &launch, &launch_pipe, nullptr}; }
+};
+
+// span-staged persistent STFT (k_stft_span): SPL = core plan (may differ from the direct kernel's: the one-exchange plans
+// the plain r2c kernels use), XS frames per tile.  Returns cudaErrorInvalidConfiguration when the tile's span does not
+// fit shared memory (very large hops): the caller falls back to the direct kernel.
+template <class PL, int X, int MINB, class SPL, int XS, int SMINB, int SPQ> struct StftSpanLaunchers : StftLaunchers<PL, X, MINB> {
+    static cudaError_t launch_span(const StftParams &sp0, cudaStream_t s) {
+        StftParams sp = sp0;
+        const size_t span = ((size_t)((long)(XS - 1) * sp.hop + sp.wsize) * sizeof(float) + 127) / 128 * 128;
+        const size_t smem = stft_work_bytes<SPL, SPQ, XS>() + 2 * span + 128 + sizeof(float2) * SPL::N;      // + mbarriers/slots + window
+        if (smem > 200u * 1024u) return cudaErrorInvalidConfiguration;
+        sp.span_bytes = (int)span;
+        const bool pad = sp.wsize < 2 * SPL::N;
+        const void *k;
+        switch (StftLaunchers<PL, X, MINB>::flavour(sp)) {
+            case STFT_K_FAST: k = pad ? (const void *)k_stft_span<SPL, XS, SPQ, SMINB, STFT_K_FAST, true> : (const void *)k_stft_span<SPL, XS, SPQ, SMINB, STFT_K_FAST, false>; break;
+            case STFT_K_EXACT: k = (const void *)k_stft_span<SPL, XS, SPQ, SMINB, STFT_K_EXACT, true>; break;
+            default: k = (const void *)k_stft_span<SPL, XS, SPQ, SMINB, STFT_K_COMPLEX, true>; break;
+        }
+        return launch_persistent_dyn(k, smem, SPL::T * XS, (sp.frames + XS - 1) / XS, sp, s);
+    }
+    static StftVariant make(const char *name) {
+        static_assert(SPL::N == PL::N, "same core size");
+        return StftVariant{name, PL::N, plan_radices<PL>(), &StftLaunchers<PL, X, MINB>::launch, &StftLaunchers<PL, X, MINB>::launch_pipe, &launch_span};
+    }
 };
 
 #define XROWS(T) ((T) >= 256 ? 1 : 256 / (T))
