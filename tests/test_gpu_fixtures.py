@@ -200,7 +200,9 @@ def test_instance_factories(wf, factory, dtype, real):
     ex = getattr(wf, factory)()
     n = 256
     rng = np.random.default_rng(3)
-    tol = 1e-12 if dtype == np.float64 else 2e-4
+    # (the reference's f64 twiddles are Taylor series good to ~5e-11, BASELINE.md section 1: neither the comparison with numpy
+    #  nor the fft -> ifft round trip is exact to machine precision)
+    tol = 1e-9 if dtype == np.float64 else 2e-4
     if real:
         ex.precompute_rfft_twiddles(n)
         buf = np.frombuffer(ex.memory.buffer, dtype, n + 2, 0)

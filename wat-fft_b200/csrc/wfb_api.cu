@@ -989,7 +989,7 @@ struct wfb_stft {
     int fft_size, wsize, hop, mode, device, flags;
     long num_samples, frames;
     const StftVariant *variant;
-    void *d_tw, *d_rtw, *d_window, *d_samples, *d_out;
+    void *d_tw, *d_tw_span, *d_rtw, *d_window, *d_samples, *d_out;
     void *h_samples, *h_out;
     size_t out_bytes;
     float db_floor, inv_range;
@@ -1013,14 +1013,18 @@ static int stft_init(wfb_stft *st) {
     CK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
     const int n = st->fft_size, m = n / 2;
     const StftVariant &v = *st->variant;
-    std::vector<float> bre, bim, fwd, rre, rim, packed, win(st->wsize);
+    std::vector<float> bre, bim, fwd, fwd_span, rre, rim, packed, win(st->wsize);
     base_twiddles<float>(TW_F32_SPLIT, m, m, bre, bim);
-    stage_tables<float>(v.radices, m, bre, bim, false, fwd);
-    if ((ilog2(m) & 1) && m >= 32 && v.radices.size() >= 2 && v.radices[0] == 2 && v.radices[1] == 4) {
-        const float c = 0.7071067811865476f;      // rfft_split's exact W_8 opening (see upload_tables)
-        const float w[3][2] = {{c, -c}, {0.f, -1.f}, {-c, -c}};
-        for (int mm = 0; mm < 3; mm++) { fwd[2 + 2 * (mm * 2 + 1)] = w[mm][0]; fwd[2 + 2 * (mm * 2 + 1) + 1] = w[mm][1]; }
-    }
+    auto tables = [&](const std::vector<int> &radices, std::vector<float> &t) {
+        stage_tables<float>(radices, m, bre, bim, false, t);
+        if ((ilog2(m) & 1) && m >= 32 && radices.size() >= 2 && radices[0] == 2 && radices[1] == 4) {
+            const float c = 0.7071067811865476f;      // rfft_split's exact W_8 opening (see upload_tables)
+            const float w[3][2] = {{c, -c}, {0.f, -1.f}, {-c, -c}};
+            for (int mm = 0; mm < 3; mm++) { t[2 + 2 * (mm * 2 + 1)] = w[mm][0]; t[2 + 2 * (mm * 2 + 1) + 1] = w[mm][1]; }
+        }
+    };
+    tables(v.radices, fwd);
+    if (!v.span_radices.empty() && v.span_radices != v.radices) tables(v.span_radices, fwd_span);   // the span kernel's core plan groups the stages differently
     base_twiddles<float>(TW_F32_SPLIT, n, m + 1, rre, rim);
     for (int k = 0; k <= m; k++) { packed.push_back(rre[k]); packed.push_back(rim[k]); }
     for (int i = 0; i < st->wsize; i++) win[i] = (float)window_value(st->mode >> 8, i, st->wsize);
@@ -1031,6 +1035,8 @@ static int stft_init(wfb_stft *st) {
     };
     int rc;
     if ((rc = up(&st->d_tw, fwd)) || (rc = up(&st->d_rtw, packed)) || (rc = up(&st->d_window, win))) return rc;
+    if (!fwd_span.empty() && (rc = up(&st->d_tw_span, fwd_span))) return rc;
+    CK(cudaDeviceSynchronize());      // the uploads above ran on the legacy stream; the plan's stream does not order against it
     if (!(st->flags & WFB_PLAN_NO_DEVICE_BUFFERS)) {
         if (cudaMalloc(&st->d_samples, st->num_samples * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
         if (cudaMalloc(&st->d_out, st->out_bytes) != cudaSuccess) { cudaGetLastError(); return WFB_ERR_ALLOC; }
@@ -1077,7 +1083,7 @@ void wfb_stft_destroy(wfb_stft *st) {
     if (!st) return;
     cudaSetDevice(st->device);
     if (st->stream) { cudaStreamSynchronize(st->stream); cudaStreamDestroy(st->stream); }
-    void *d[] = {st->d_tw, st->d_rtw, st->d_window, st->d_samples, st->d_out};
+    void *d[] = {st->d_tw, st->d_tw_span, st->d_rtw, st->d_window, st->d_samples, st->d_out};
     for (void *p : d) if (p) cudaFree(p);
     if (st->h_samples) cudaFreeHost(st->h_samples);
     if (st->h_out) cudaFreeHost(st->h_out);
@@ -1111,11 +1117,14 @@ int wfb_stft_exec_device(wfb_stft *st, const float *d_samples, void *d_out, void
     cudaStream_t cs = stream ? (cudaStream_t)stream : st->stream;
     // span kernel: whole tiles of overlapping frames as one bulk copy (16-byte aligned frame starts and sizes)
     const char *span_env = getenv("WFB_STFT_SPAN");             // (read per call: tests and A/B runs flip it)
-    const bool span_on = !span_env || atoi(span_env) != 0;
+    const bool span_on = span_env ? atoi(span_env) != 0 : st->variant->span_default;      // WFB_STFT_SPAN=1 forces, =0 forbids
     cudaError_t e = cudaErrorInvalidConfiguration;
     if (span_on && st->variant->launch_span && st->hop % 4 == 0 && st->wsize % 4 == 0 && ((uintptr_t)d_samples % 16) == 0 &&
-        ((uintptr_t)d_out % 16) == 0)
-        e = st->variant->launch_span(sp, cs);
+        ((uintptr_t)d_out % 16) == 0) {
+        StftParams ss = sp;
+        if (st->d_tw_span) ss.tw = st->d_tw_span;
+        e = st->variant->launch_span(ss, cs);
+    }
     if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); e = (pipe ? st->variant->launch_pipe : st->variant->launch)(sp, cs); }
     if (e != cudaSuccess) return cuda_fail(e, "stft launch");
     return WFB_OK;

@@ -2098,7 +2098,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(const __grid_const
 // ----------------------------------------------------------------------------------------
 // Span-staged persistent STFT (the default when hop and window are multiples of 4 samples).
 //   * The X frames of a tile overlap, so their samples are ONE contiguous span of (X-1)*hop + window floats: it arrives
-//     as ONE bulk copy (double-buffered, prefetched a tile ahead) and every frame is formed out of shared memory.  The
+//     as ONE bulk copy (prefetched while the previous tile is computed) and every frame is formed out of shared memory.  The
 //     direct kernel above re-loads every sample window/hop times through the L1 data pipe, its top-utilised unit.
 //   * The window function sits in shared memory for the whole kernel (the direct kernel re-loads it from global memory
 //     for every frame, through the tagged L1 path).
@@ -2106,7 +2106,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_pipe(const __grid_const
 //     one bulk store.  Rows are (M+1) floats, so a tile starts at any multiple of 4 bytes: the tile is assembled at the
 //     same 16-byte phase as its destination, the aligned interior goes out as a bulk store and the <= 3 floats at either
 //     end as plain stores.
-// Shared memory: [work: X padded scratch rows, reused for the result tile][span stage 0][span stage 1][mbarriers, slots][window].
+// Shared memory: [work: X padded scratch rows, reused for the result tile][span][mbarrier, slots][window].
 // ----------------------------------------------------------------------------------------
 template <class PL, int PADQ, int X> __host__ __device__ constexpr size_t stft_work_bytes() {
     size_t a = sizeof(cx<float>) * (size_t)padded_size<PADQ>(PL::N) * X + 16;      // + the output phase offset
@@ -2164,10 +2164,10 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_span(const __grid_const
     constexpr int M = PL::N, T = PL::T, E = PL::E, PER = E / 2, HALF = M / 2;
     constexpr int LAST = PL::npass() - 1;
     constexpr size_t WORK = stft_work_bytes<PL, PADQ, X>();
-    const uint32_t span_cap = (uint32_t)sp.span_bytes;                   // bytes per span stage (multiple of 128)
+    const uint32_t span_cap = (uint32_t)sp.span_bytes;                   // bytes of the span buffer (multiple of 128)
     unsigned char *work = smem_raw;
     unsigned char *span = smem_raw + WORK;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + WORK + 2 * (size_t)span_cap);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + WORK + (size_t)span_cap);
     long *slot = reinterpret_cast<long *>(mbar + 4);
     const int xi = threadIdx.x / T, tid = threadIdx.x % T;
     const float2 *tw = reinterpret_cast<const float2 *>(sp.tw);
@@ -2177,14 +2177,13 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_span(const __grid_const
     float *gout = reinterpret_cast<float *>(sp.out);
 
     if (threadIdx.x == 0) {
-        mbar_init(mbar + 0, 1);
-        mbar_init(mbar + 1, 1);
+        mbar_init(mbar, 1);
         fence_proxy_async();
     }
     // the window function, once per CTA, in shared memory behind the span stages (zero beyond the window): the frames are
     // formed with two conflict-free LDS.64 per value pair.  (Holding each thread's window values in registers for the whole
     // kernel was measured first: 64 more registers on the 32-value plans, 8 warps per SM, 8 % slower than the direct kernel.)
-    float2 *winsm = reinterpret_cast<float2 *>(smem_raw + WORK + 2 * (size_t)span_cap + 128);
+    float2 *winsm = reinterpret_cast<float2 *>(smem_raw + WORK + (size_t)span_cap + 128);
     {
         const float2 *w2 = reinterpret_cast<const float2 *>(sp.window);
         for (int pidx = threadIdx.x; pidx < M; pidx += T * X)
@@ -2193,11 +2192,13 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_span(const __grid_const
     __syncthreads();
 
     auto tile_rows = [&](long tile) { const long f0 = tile * X; return (sp.frames - f0 < X) ? (int)(sp.frames - f0) : X; };
-    auto issue = [&](long tile, int st) {
+    // ONE span buffer: a tile's samples are consumed (into registers) at the very start of its iteration, so the next
+    // tile's span is fetched into the same bytes while this tile is computed
+    auto issue = [&](long tile, int) {
         if (threadIdx.x == 0) {
             const uint32_t bytes = (uint32_t)(((long)(tile_rows(tile) - 1) * sp.hop + sp.wsize) * sizeof(float));
-            mbar_expect_tx(mbar + st, bytes);
-            tma_load_1d(span + (size_t)st * span_cap, sp.samples + tile * X * (long)sp.hop, bytes, mbar + st);
+            mbar_expect_tx(mbar, bytes);
+            tma_load_1d(span, sp.samples + tile * X * (long)sp.hop, bytes, mbar);
         }
     };
     // the result tile of `tile` sits in `work` at the 16-byte phase of its destination
@@ -2230,11 +2231,11 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_span(const __grid_const
         if (prev_tile >= 0) store_tile(prev_tile);
         const long tile = slot[st];
         if (tile >= tiles) break;
-        mbar_wait(mbar + st, (phasebits >> st) & 1u);
-        phasebits ^= 1u << st;
+        mbar_wait(mbar, phasebits);
+        phasebits ^= 1u;
         const long frame = tile * X + xi;
         // hop is a multiple of 4 samples: every frame starts on a 16-byte boundary of the span
-        const float2 *raw = reinterpret_cast<const float2 *>(span + (size_t)st * span_cap) + (size_t)xi * (sp.hop >> 1);
+        const float2 *raw = reinterpret_cast<const float2 *>(span) + (size_t)xi * (sp.hop >> 1);
         static_for<E>([&](auto E_) {
             CIDX(e, E_);
             const int pidx = tid + e * T;
@@ -2244,8 +2245,9 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_stft_span(const __grid_const
             x[e] = mk<R>(v.x * w.x, v.y * w.y);
         });
         if (threadIdx.x == 0) bulk_wait_read_all();                     // the last result tile has left `work` ...
+        fence_proxy_async();                                             // (our reads of the span precede its refill by the copy engine)
         __syncthreads();                                                 // ... before anyone uses it as scratch; all span reads done
-        claim_and_issue<false>(sp.ctr, pending, tiles, slot, st ^ 1, issue);   // (the other stage was consumed an iteration ago)
+        claim_and_issue<false>(sp.ctr, pending, tiles, slot, st ^ 1, issue);   // next tile's span, while this tile is computed
         cx<R> *scratch = reinterpret_cast<cx<R> *>(work) + (size_t)xi * padded_size<PADQ>(M);
         run_all<R, PL, PADQ, X, false>(x, tw, GTw<R>{nullptr, tw}, scratch, tid, xi, false);
         if (PL::npass() > 1) sync_transform<T, X>(xi);

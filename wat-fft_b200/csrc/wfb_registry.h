@@ -179,7 +179,11 @@ template <class PL, int X, int MINB> struct RealTileLaunchers {
 
 // fused STFT (frame gather + window + r2c + magnitude/dB)
 typedef cudaError_t (*stft_launch_fn)(const StftParams &sp, cudaStream_t s);
-struct StftVariant { const char *name; int core_n; std::vector<int> radices; stft_launch_fn launch, launch_pipe, launch_span; };
+struct StftVariant {
+    const char *name; int core_n; std::vector<int> radices; stft_launch_fn launch, launch_pipe, launch_span;
+    std::vector<int> span_radices;     // stage structure of the span kernel's core plan (its own twiddle table when it differs)
+    bool span_default = false;         // measured faster than the direct kernel at hop = N/4 (profiles/): used unless WFB_STFT_SPAN says otherwise
+};
 // persistent launch whose dynamic shared memory varies from call to call (the span stages depend on hop and window)
 cudaError_t launch_persistent_dyn(const void *kernel, size_t smem, int threads, long work_items, const StftParams &sp, cudaStream_t s);
 cudaError_t launch_persistent_raw(const void *kernel, size_t smem, int threads, long work_items, void *params, cudaStream_t s);
@@ -216,17 +220,17 @@ template <class PL, int X, int MINB, int PQ = PADQ> struct StftLaunchers {
         }
         return launch_persistent_raw(k, smem_pipe, PL::T * XP, (sp.frames + XP - 1) / XP, (void *)&sp, s);
     }
-    static StftVariant make(const char *name) { return StftVariant{name, PL::N, plan_radices<PL>(), &launch, &launch_pipe, nullptr}; }
+    static StftVariant make(const char *name) { return StftVariant{name, PL::N, plan_radices<PL>(), &launch, &launch_pipe, nullptr, {}}; }
 };
 
 // span-staged persistent STFT (k_stft_span): SPL = core plan (may differ from the direct kernel's: the one-exchange plans
 // the plain r2c kernels use), XS frames per tile.  Returns cudaErrorInvalidConfiguration when the tile's span does not
 // fit shared memory (very large hops): the caller falls back to the direct kernel.
-template <class PL, int X, int MINB, class SPL, int XS, int SMINB, int SPQ> struct StftSpanLaunchers : StftLaunchers<PL, X, MINB> {
+template <class PL, int X, int MINB, class SPL, int XS, int SMINB, int SPQ, bool DEFAULT> struct StftSpanLaunchers : StftLaunchers<PL, X, MINB> {
     static cudaError_t launch_span(const StftParams &sp0, cudaStream_t s) {
         StftParams sp = sp0;
         const size_t span = ((size_t)((long)(XS - 1) * sp.hop + sp.wsize) * sizeof(float) + 127) / 128 * 128;
-        const size_t smem = stft_work_bytes<SPL, SPQ, XS>() + 2 * span + 128 + sizeof(float2) * SPL::N;      // + mbarriers/slots + window
+        const size_t smem = stft_work_bytes<SPL, SPQ, XS>() + span + 128 + sizeof(float2) * SPL::N;      // + mbarriers/slots + window
         if (smem > 200u * 1024u) return cudaErrorInvalidConfiguration;
         sp.span_bytes = (int)span;
         const bool pad = sp.wsize < 2 * SPL::N;
@@ -240,7 +244,7 @@ template <class PL, int X, int MINB, class SPL, int XS, int SMINB, int SPQ> stru
     }
     static StftVariant make(const char *name) {
         static_assert(SPL::N == PL::N, "same core size");
-        return StftVariant{name, PL::N, plan_radices<PL>(), &StftLaunchers<PL, X, MINB>::launch, &StftLaunchers<PL, X, MINB>::launch_pipe, &launch_span};
+        return StftVariant{name, PL::N, plan_radices<PL>(), &StftLaunchers<PL, X, MINB>::launch, &StftLaunchers<PL, X, MINB>::launch_pipe, &launch_span, plan_radices<SPL>(), DEFAULT};
     }
 };
 
