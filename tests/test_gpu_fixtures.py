@@ -122,6 +122,67 @@ def test_full_size_properties_r2c(wf, oracle, n):
     plan.destroy()
 
 
+@pytest.mark.parametrize("n", [256, 1024, 4096])
+def test_full_size_properties_f64(wf, oracle, n):
+    """BASELINE config 4 at full size (batch = 2^30 / 16N): f64 c2c rows against the oracle with the 1e-14*log2(N) bound,
+    Parseval and the round trip over the whole batch; f64 r2c rows against the oracle, c2r(r2c(x)) = x over the whole batch."""
+    import torch
+    C = wf._cabi
+    batch = (1 << 30) // (16 * n)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(n)
+    flags = C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS
+    z = torch.rand(batch * 2 * n, device=dev, generator=g, dtype=torch.float64) * 2 - 1
+    out = torch.empty_like(z)
+    plan = wf.Plan(C.C2C, C.F64, C.INTERLEAVED, n, batch, 0, flags)
+    plan.exec_device(C.FORWARD, (z.data_ptr(), None), (out.data_ptr(), None))
+    plan.sync()
+    for r in sorted({0, 1, batch // 2, batch - 1}):
+        a = z[r * 2 * n:(r + 1) * 2 * n].cpu().numpy()
+        assert rel_err(out[r * 2 * n:(r + 1) * 2 * n].cpu().numpy(), oracle.fft_f64(a), a) <= f64_bound(n), (n, r)
+    assert abs(float((out ** 2).sum()) / (n * float((z ** 2).sum())) - 1) < 1e-9
+    plan.exec_device(C.INVERSE, (out.data_ptr(), None), (out.data_ptr(), None))         # in place
+    plan.sync()
+    assert float((out - z).abs().max()) < 1e-9          # (Taylor-series twiddles: the round trip is good to ~1e-10, not 1e-16)
+    plan.destroy()
+    x = z[: batch * n]
+    spec = out[: batch * (n + 2)]
+    back = torch.empty_like(x)
+    plan = wf.Plan(C.R2C, C.F64, 0, n, batch, 0, flags)
+    plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
+    plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))
+    plan.sync()
+    for r in sorted({0, batch // 2, batch - 1}):
+        a = x[r * n:(r + 1) * n].cpu().numpy()
+        assert rel_err(spec[r * (n + 2):(r + 1) * (n + 2)].cpu().numpy(), oracle.rfft_f64(a), a) <= f64_bound(n), (n, r)
+    assert float((back - x).abs().max()) < 1e-9
+    plan.destroy()
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 256, 1024, 4096, 16384])
+def test_c2r_f64_against_the_f64_dft(wf, n):
+    """f64 c2r has no reference implementation (parity unpinned by definition), so it is gated against the f64
+    truth itself: for a Hermitian spectrum built by numpy from random x, c2r must return x (numpy.fft.irfft semantics, 1/n
+    normalised), at every size and for a batch; the imaginary parts of DC and Nyquist are ignored like irfft_split does."""
+    rng = np.random.default_rng(n)
+    batch = 5
+    x = rng.uniform(-1, 1, (batch, n))
+    spec = np.fft.rfft(x, axis=-1)                        # exact (to 1e-16) Hermitian half spectra
+    il = np.empty((batch, n + 2))
+    il[:, 0::2], il[:, 1::2] = spec.real, spec.imag
+    il[:, 1] = 123.0                                      # garbage in the DC / Nyquist imaginary parts must not matter
+    il[:, n + 1] = -7.0
+    c = wf.createRFFT(n, batch=batch)
+    c.getOutputBuffer()[:] = il.ravel()
+    c.inverse()
+    got = c.getInputBuffer().reshape(batch, n).copy()
+    c.dispose()
+    # the c2r core multiplies by the Taylor-series twiddles of the reference's f64 modules (accurate to ~5e-11)
+    assert np.max(np.abs(got - x)) < 2e-9 * math.log2(n)
+    assert np.max(np.abs(got - np.fft.irfft(spec, n=n, axis=-1))) < 2e-9 * math.log2(n)
+
+
 def test_sharded_context_single_device(wf):
     from watfft_b200.sharding import ShardedSplitFFT
     n, batch = 256, 19

@@ -196,8 +196,10 @@ def test_output_order(be, n):
     sig = sum((k + 1) * np.exp(2j * np.pi * k * t / n) for k in range(n)) / n
     got = cx(be.fft_f64(il(sig)[None]))[0]
     assert np.max(np.abs(got - (np.arange(n) + 1))) < max(1e-4, n * 1e-7)
+    # (not in the reference's suite, which runs this signal through the f64 module only: the same permutation check on the
+    #  f32 split module, with north_star's f32 bound max|err| <= 2e-6 * log2(n) * ||x||_2 instead of a tolerance of our own)
     re, im = be.fft_split_f32(sig.real[None].astype(np.float32), sig.imag[None].astype(np.float32))
-    assert np.max(np.abs((re[0] + 1j * im[0]) - (np.arange(n) + 1))) < max(1e-4, n * 1e-6) * 8
+    assert np.max(np.abs((re[0] + 1j * im[0]) - (np.arange(n) + 1))) <= 2e-6 * math.log2(n) * np.linalg.norm(sig)
     # f32 vs f64 consistency (seed 789+n)
     if n >= 32:
         xr = om.lcg_signal(n, 789 + n)
@@ -257,7 +259,7 @@ def test_split_and_dual_forward_vs_dft(be, n):
     assert np.max(np.abs((gr + 1j * gi) - truth)) < 5e-3                                  # :78-114
     x = np.empty((2, 2 * n), np.float32)
     x[:, 0::2], x[:, 1::2] = re, im
-    assert np.max(np.abs(cx(be.fft_interleaved_f32(x)) - truth)) < max(1e-4 * math.sqrt(n / 1024), 2e-5) * 8   # :52
+    assert np.max(np.abs(cx(be.fft_interleaved_f32(x)) - truth)) < 1e-4 * math.sqrt(n / 1024)   # tests/fft_f32_dual.test.js:83-86, as is
 
 
 @pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])

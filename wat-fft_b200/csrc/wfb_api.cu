@@ -390,6 +390,12 @@ static int upload_tables(wfb_plan *pl, int vi) {
     if (sizeof(R) == 8) flavour = (m == 16 || m <= 4) ? TW_EXACT : TW_F64;
     else if (pl->kind == WFB_C2C && pl->layout == WFB_INTERLEAVED) flavour = (m <= 16) ? TW_EXACT : TW_F32_DUAL;
     else flavour = TW_F32_SPLIT;
+    // Kernels that DERIVE w2 = w1^2, w3 = w1*w2 in registers (f32 scalar lanes, core >= WFB_DERIVE_MIN_N: derive_tw in
+    // wfb_kernels.cuh) square and cube whatever error w1 carries.  The reference's f32 table is a 6-term Taylor series good to
+    // ~5e-7; derived from it, w3 is off by 1.5e-6 and N = 4096 misses the reference's own absolute threshold
+    // (tests/fft_f32_dual.test.js:83-86: 2.6e-4 against 2.0e-4).  So those kernels get CORRECTLY ROUNDED w1 (error 6e-8): the
+    // derived factors are then more accurate than the reference's looked-up ones, and the f32 contract is tolerance-based.
+    if (sizeof(R) == 4 && v.lanes == 1 && m >= WFB_DERIVE_MIN_N) flavour = TW_EXACT;
     std::vector<R> bre, bim, fwd, inv;
     base_twiddles<R>(flavour, m, m, bre, bim);
     stage_tables<R>(v.radices, m, bre, bim, false, fwd);
@@ -1014,7 +1020,7 @@ static int stft_init(wfb_stft *st) {
     const int n = st->fft_size, m = n / 2;
     const StftVariant &v = *st->variant;
     std::vector<float> bre, bim, fwd, fwd_span, rre, rim, packed, win(st->wsize);
-    base_twiddles<float>(TW_F32_SPLIT, m, m, bre, bim);
+    base_twiddles<float>(m >= WFB_DERIVE_MIN_N ? TW_EXACT : TW_F32_SPLIT, m, m, bre, bim);      // (derived w2, w3: see upload_tables)
     auto tables = [&](const std::vector<int> &radices, std::vector<float> &t) {
         stage_tables<float>(radices, m, bre, bim, false, t);
         if ((ilog2(m) & 1) && m >= 32 && radices.size() >= 2 && radices[0] == 2 && radices[1] == 4) {

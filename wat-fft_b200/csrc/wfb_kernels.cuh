@@ -252,8 +252,42 @@ template <typename R, class PL> __host__ __device__ constexpr bool derive_tw() {
 // ----------------------------------------------------------------------------------------
 // one fused pass over the E register-resident values of a thread
 // ----------------------------------------------------------------------------------------
-template <typename R, class PL, int P, bool INV, class U>
-__device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, const U &tw0, int tid) {
+// Last-pass twiddles held in registers across the tiles of a persistent kernel ("hoisting").  In the last pass every
+// thread multiplies by table entries only it uses (group index = thread index): 15 complex values per 16-point block
+// that are the same for every transform the thread ever processes.  Re-loading them per tile is a third of the L1 data
+// pipe traffic of the f64 real kernels (ncu, profiles/r02_ncu_full.md: r2c f64 N = 2048 at 84 % L1 pipe, a quarter of the
+// wavefronts twiddle LDG.128s); the f64 CTAs are small (64-256 threads, 1-4 per SM), so the registers are there.
+//   hoist_count: entries per thread;  hoist_index: register of (block i, sub-stage q, digit prefix hi, input m >= 1)
+template <typename R, class PL, int P> __host__ __device__ constexpr int hoist_per_block() {
+    int n = 0;
+    for (int q = 0; q < pass_nsub(PL::code(P)); q++) n += hi_count(PL::code(P), q) * (pass_radix(PL::code(P), q) - 1);
+    return n;
+}
+template <typename R, class PL, int P> __host__ __device__ constexpr int hoist_count() {
+    return hoist_per_block<R, PL, P>() * (PL::E / pass_rp(PL::code(P)));
+}
+template <typename R, class PL, int P> __host__ __device__ constexpr int hoist_index(int i, int q, int hi, int m) {
+    int base = 0;
+    for (int a = 0; a < q; a++) base += hi_count(PL::code(P), a) * (pass_radix(PL::code(P), a) - 1);
+    return i * hoist_per_block<R, PL, P>() + base + hi * (pass_radix(PL::code(P), q) - 1) + (m - 1);
+}
+struct NoHoist { static constexpr bool ON = false; };
+template <typename R> struct Hoisted {
+    static constexpr bool ON = true;
+    const typename RT<R>::twel *regs;
+    template <int I> __device__ __forceinline__ twd<R> at() const { const typename RT<R>::twel t = regs[I]; return {t.x, t.y, -t.y}; }
+};
+
+template <typename R, class PL, int P, int I, int Q, int HI, int RADIX, class HS>
+__device__ __forceinline__ void hoisted_get(const HS &hs, twd<R> &w1, twd<R> &w2, twd<R> &w3) {
+    if constexpr (HS::ON) {
+        w1 = hs.template at<hoist_index<R, PL, P>(I, Q, HI, 1)>();
+        if constexpr (RADIX == 4) { w2 = hs.template at<hoist_index<R, PL, P>(I, Q, HI, 2)>(); w3 = hs.template at<hoist_index<R, PL, P>(I, Q, HI, 3)>(); }
+    }
+}
+
+template <typename R, class PL, int P, bool INV, class U, class HS = NoHoist>
+__device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, const U &tw0, int tid, const HS &hs = HS()) {
     constexpr int CODE = PL::code(P);
     constexpr int RP = pass_rp(CODE);
     constexpr int NB = PL::E / RP;                 // register blocks per thread
@@ -282,6 +316,9 @@ __device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>
                 if constexpr (!unit && L_IN == 1) {           // thread-independent: constant operands
                     w1 = tw0.template at<off + c>();
                     if constexpr (r == 4) { w2 = tw0.template at<off + lq + c>(); w3 = tw0.template at<off + 2 * lq + c>(); }
+                } else if constexpr (!unit && HS::ON) {
+                    static_assert(!HS::ON || !derive_tw<R, PL>(), "hoisting keeps table entries, not derived ones");
+                    hoisted_get<R, PL, P, i, q, hi, r>(hs, w1, w2, w3);
                 } else if constexpr (!unit) {
                     w1 = ld_tw(twj + (off + L_IN * c));
                     if constexpr (r == 4) {
@@ -323,6 +360,36 @@ __device__ __forceinline__ void run_pass(cx<R> (&x)[PL::E], const typename RT<R>
                         B = INV ? m3 : m1;
                         D = INV ? m1 : m3;
                     }
+                });
+            });
+        });
+    });
+}
+
+// fills the hoisted registers of pass P: the very table entries run_pass would load, in hoist_index order
+template <typename R, class PL, int P>
+__device__ __forceinline__ void hoist_load(typename RT<R>::twel (&hw)[hoist_count<R, PL, P>()], const typename RT<R>::twel *__restrict__ tw, int tid) {
+    constexpr int CODE = PL::code(P);
+    constexpr int RP = pass_rp(CODE);
+    constexpr int NB = PL::E / RP;
+    constexpr int L_IN = PL::l_in(P);
+    constexpr int SP = PL::N / (L_IN * RP);
+    static_assert(L_IN > 1, "pass 0 has no thread-dependent twiddles");
+    static_for<NB>([&](auto I_) {
+        CIDX(i, I_);
+        const int j = (tid + i * PL::T) / SP;
+        static_for<pass_nsub(CODE)>([&](auto Q_) {
+            CIDX(q, Q_);
+            constexpr int r = pass_radix(CODE, q);
+            constexpr int H = hi_count(CODE, q);
+            constexpr int lq = L_IN * H;
+            constexpr int off = PL::tw_off(P, q);
+            static_for<H>([&](auto HI_) {
+                CIDX(hi, HI_);
+                constexpr int c = hi_to_c(CODE, q, hi);
+                static_for<r - 1>([&](auto M_) {
+                    CIDX(m0, M_);
+                    hw[hoist_index<R, PL, P>(i, q, hi, m0 + 1)] = __ldg(tw + j + (off + m0 * lq + L_IN * c));
                 });
             });
         });
@@ -377,16 +444,17 @@ __device__ __forceinline__ void fill_inputs(cx<R> (&x)[PL::E], const cx<R> *sm, 
 
 // all passes; on entry x holds pass 0's inputs (element tid + e*T in slot e), on exit the last
 // pass's outputs.  `smem_dirty`: other threads may still be reading smem when we get here.
-template <typename R, class PL, int PADQ, int X, bool INV, int P = 0, class U>
+template <typename R, class PL, int PADQ, int X, bool INV, int P = 0, class U, class HS = NoHoist>
 __device__ __forceinline__ void run_all(cx<R> (&x)[PL::E], const typename RT<R>::twel *__restrict__ tw, const U &tw0, cx<R> *sm,
-                                        int tid, int xi, bool smem_dirty) {
-    run_pass<R, PL, P, INV>(x, tw, tw0, tid);
+                                        int tid, int xi, bool smem_dirty, const HS &hs = HS()) {
+    if constexpr (HS::ON && P + 1 == PL::npass() && P > 0) run_pass<R, PL, P, INV>(x, tw, tw0, tid, hs);   // hoisted: the last pass
+    else run_pass<R, PL, P, INV>(x, tw, tw0, tid);
     if constexpr (P + 1 < PL::npass()) {
         if (smem_dirty || P > 0) sync_transform<PL::T, X>(xi);
         spill_outputs<R, PL, P, PADQ>(x, sm, tid);
         sync_transform<PL::T, X>(xi);
         fill_inputs<R, PL, P + 1, PADQ>(x, sm, tid);
-        run_all<R, PL, PADQ, X, INV, P + 1>(x, tw, tw0, sm, tid, xi, true);
+        run_all<R, PL, PADQ, X, INV, P + 1>(x, tw, tw0, sm, tid, xi, true, hs);
     }
 }
 
@@ -928,7 +996,7 @@ template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr s
 // stores issued after the next loop-top barrier, instead of per-thread STG; the stage is refilled once those
 // stores have drained (cp.async.bulk.wait_group.read), which the issuing lanes check after the row loads of the
 // following tile.
-template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, bool RC = false, bool TS = false>
+template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, bool RC = false, bool TS = false, bool HT = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     static_assert(!TS || RT<R>::LANES == 1, "TMA stores: scalar lanes");
@@ -1019,8 +1087,12 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
     long pending = claim_prime<(PL::N <= 256)>(p.ctr);
     claim_and_issue<(PL::N <= 256)>(p.ctr, pending, tiles, slot, 0, issue);
     cx<R> x[PL::E];
-    // (hoisting the last pass's thread-invariant twiddles into registers was tried and measured
-    //  neutral at N = 4096 and 3-6 % slower below, from the extra 27 registers: profiles/r01_sweep.md)
+    // HT: the last pass's thread-invariant twiddles live in registers for the whole kernel (see hoist_load).  For the f32
+    // kernels this measured neutral at N = 4096 and 3-6 % slower below (profiles/r01_sweep.md); the f64 kernels are bound by
+    // the L1 data pipe these loads go through, and their small CTAs have the registers to spare.
+    typename RT<R>::twel hw[HT ? hoist_count<R, PL, (LAST > 0 ? LAST : 1)>() : 1];
+    if constexpr (HT) { static_assert(LAST > 0, "hoisting needs a multi-pass plan"); hoist_load<R, PL, LAST>(hw, tw, tid); }
+    const auto hsrc = [&]() { if constexpr (HT) return Hoisted<R>{hw}; else return NoHoist{}; }();
     for (int it = 0;; it++) {
         const int st = it & 1;
         fence_proxy_async();      // our generic-proxy accesses to the other stage precede its refill
@@ -1067,7 +1139,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         // TS: slot[st ^ 1] still names the tile just stored; the claim overwrites it only now, after the barrier
         if constexpr (TS) claim_and_issue<(PL::N <= 256)>(p.ctr, pending, tiles, slot, st ^ 1, issue);
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(N);
-        run_all<R, PL, PADQ, X, INV>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
+        run_all<R, PL, PADQ, X, INV>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false, hsrc);
 
         if constexpr (TS) {
             // results -> the tile's rows in the stage buffer (they alias every group's scratch)
@@ -1303,7 +1375,7 @@ template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ c
 // bulk store after the next loop-top barrier.  r2c: each row's (M+1) bins; the mirrored halves are parked in the
 // row's own slots [1, M/2], and the thread that reads park[k] is the one that overwrites it with X[k], so the
 // post-process is in place.  c2r: the M complex (= N real) outputs of each row.
-template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false, bool TS = false>
+template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false, bool TS = false, bool HT = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
     static_assert(!C2R || X % 2 == 0 || X == 1 || sizeof(R) == 8, "f32 c2r tiles: an even number of rows (16-byte alignment), or single rows");
@@ -1403,6 +1475,9 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     long pending = claim_prime<false>(p.ctr);
     claim_and_issue<false>(p.ctr, pending, tiles, slot, 0, issue);
     cx<R> x[PL::E];
+    typename RT<R>::twel hw[HT ? hoist_count<R, PL, (LAST > 0 ? LAST : 1)>() : 1];      // HT: see k_c2c_pipe
+    if constexpr (HT) { static_assert(LAST > 0, "hoisting needs a multi-pass plan"); hoist_load<R, PL, LAST>(hw, tw, tid); }
+    const auto hsrc = [&]() { if constexpr (HT) return Hoisted<R>{hw}; else return NoHoist{}; }();
     unsigned phasebits = 0;                            // mbarrier phase parity per stage (bit st)
     for (int it = 0;; it++) {
         const int st = it & 1;
@@ -1432,7 +1507,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             static_for<PL::E>([&](auto E_) { CIDX(e, E_); const V2 a = raw[tid + e * PL::T]; x[e] = mk<R>(a.x, a.y); });
             __syncthreads();                           // dense tile and padded scratch alias
             if constexpr (TS) claim_and_issue<false>(p.ctr, pending, tiles, slot, st ^ 1, issue);   // (slot[st ^ 1] was read before the barrier)
-            run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false);
+            run_all<R, PL, PADQ, X, false>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, false, hsrc);
             // TS: the result rows are dense ([X][M+1]) and alias the other groups' scratch
             cx<R> *park = TS ? reinterpret_cast<cx<R> *>(buf) + (size_t)xr * (M + 1) + (ROW1 ? (int)(tile & 1) : 0) : scratch;
             if (PL::npass() > 1) { if constexpr (TS && X > 1) __syncthreads(); else sync_transform<PL::T, X>(xi); }
@@ -1507,7 +1582,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             });
             sync_transform<PL::T, X>(xi);
             static_for<PER>([&](auto E_) { CIDX(e, E_); x[PER + e] = scratch[M - (PER + e) * PL::T - tid]; });
-            run_all<R, PL, PADQ, X, true>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, true);
+            run_all<R, PL, PADQ, X, true>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, true, hsrc);
             if constexpr (TS) {
                 if constexpr (X > 1) __syncthreads(); else sync_transform<PL::T, X>(xi);   // result rows alias the scratch
                 V2 *z = reinterpret_cast<V2 *>(buf) + (size_t)xi * M + tid;

@@ -79,16 +79,16 @@ template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers
 };
 
 // persistent TMA-pipelined c2c: grid = resident CTAs, each loops over tiles of X*LANES rows
-template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false> struct PipeLaunchers {
+template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false, bool HT = false> struct PipeLaunchers {
     static constexpr size_t smem = 2 * pipe_buf_bytes<R, PL, PQ, X>() + 64;
     static constexpr int LANES = RT<R>::LANES;
     static long tiles(long batch) { return (batch + X * LANES - 1) / (X * LANES); }
     static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
         const void *k;
         if (io == IO_SPLIT)
-            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PQ, IO_SPLIT, true, MINB, RC, TS> : (const void *)k_c2c_pipe<R, PL, X, PQ, IO_SPLIT, false, MINB, RC, TS>;
+            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PQ, IO_SPLIT, true, MINB, RC, TS, HT> : (const void *)k_c2c_pipe<R, PL, X, PQ, IO_SPLIT, false, MINB, RC, TS, HT>;
         else
-            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, true, MINB, RC, TS> : (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, false, MINB, RC, TS>;
+            k = dir ? (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, true, MINB, RC, TS, HT> : (const void *)k_c2c_pipe<R, PL, X, PQ, IO_INTERLEAVED, false, MINB, RC, TS, HT>;
         return launch_persistent(k, smem, PL::T * X, tiles(batch), p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
@@ -98,14 +98,14 @@ template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ,
 
 // persistent TMA-pipelined r2c / c2r (scalar lanes)
 // XI: rows per tile of the c2r direction (1 = single-row tiles with shifted bulk copies, see k_real_pipe)
-template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false, int XI = X> struct RealPipeLaunchers {
+template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false, int XI = X, bool HT = false> struct RealPipeLaunchers {
     static constexpr size_t smem_f = 2 * real_pipe_buf_bytes<R, PL, PQ, X, false>() + 64;
     static constexpr size_t smem_i = 2 * real_pipe_buf_bytes<R, PL, PQ, XI, true>() + 64;
     static cudaError_t r2c(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_persistent((const void *)k_real_pipe<R, PL, X, PQ, false, MINB, RC, TS>, smem_f, PL::T * X, (batch + X - 1) / X, p, s);
+        return launch_persistent((const void *)k_real_pipe<R, PL, X, PQ, false, MINB, RC, TS, HT>, smem_f, PL::T * X, (batch + X - 1) / X, p, s);
     }
     static cudaError_t c2r(int, int, const KParams &p, long batch, cudaStream_t s) {
-        return launch_persistent((const void *)k_real_pipe<R, PL, XI, PQ, true, MINB, false, TS>, smem_i, PL::T * XI, (batch + XI - 1) / XI, p, s);
+        return launch_persistent((const void *)k_real_pipe<R, PL, XI, PQ, true, MINB, false, TS, HT>, smem_i, PL::T * XI, (batch + XI - 1) / XI, p, s);
     }
     static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
         return Variant{name, PL::N, PL::T * X, X, smem_i > smem_f ? smem_i : smem_f, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, 16, plan_radices<PL>(), nullptr, &r2c, &c2r};

@@ -5,6 +5,12 @@ namespace wfb {
 #define VR(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB>::make(#PL "_rpipe" #X, __VA_ARGS__)
 #define VTS(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_pipe" #X "_ts", PRIO)
 #define VRTS(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_rpipe" #X "_ts", __VA_ARGS__)
+// + the last pass's twiddles held in registers across tiles (HT, see hoist_load in wfb_kernels.cuh)
+#define VTSH(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB, false, PADQ, true, true>::make(#PL "_pipe" #X "_ts_ht", PRIO)
+#define VRTSH(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true, X, true>::make(#PL "_rpipe" #X "_ts_ht", __VA_ARGS__)
+// + a higher minimum of resident CTAs (the register cap that goes with it): the f64 real kernels run 8 warps per SM
+#define VRTSM(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_rpipe" #X "_ts_m" #MINB, __VA_ARGS__)
+#define VRTSHM(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true, X, true>::make(#PL "_rpipe" #X "_ts_ht_m" #MINB, __VA_ARGS__)
 const std::vector<Variant> &variants_f64_pipe() {
     // priorities from the sweeps in profiles/ (c2c N = 256: the direct kernel wins; real transforms: the pipelined
     // kernels win up to N = 2048 since the Hermitian step moves only half its data through shared memory)
@@ -20,6 +26,10 @@ const std::vector<Variant> &variants_f64_pipe() {
         // one exchange instead of two at M = 512 (r2c f64 N = 1024: 79 -> 92 %, c2r: 93 -> 104 %); the radix-4 cores (M = 1024,
         // 4096) and M = 2048 do not factor into two passes of <= 32 values per thread
         VRTS(D32_512, 2, 1, 62),
+        // hoisted last-pass twiddles where the L1 data pipe is the bound (ncu r02: 84 % at r2c N = 2048, 78 % at 4096, 71 % at c2c 4096)
+        VTSH(F64_1024, 1, 2, 40), VTSH(F64_2048, 1, 2, 40), VTSH(F64_4096, 1, 1, 40),
+        VRTSH(D32_512, 2, 1, 40), VRTSH(F64_1024, 1, 2, 40), VRTSH(F64_2048, 1, 1, 40),
+        VRTSM(F64_1024, 1, 6, 39), VRTSHM(F64_1024, 1, 6, 39), VRTSM(F64_2048, 1, 3, 39), VRTSHM(F64_2048, 1, 3, 39), VRTSM(F64_512, 2, 8, 39),
         VR(F64_128, 16, 2, 30), VR(F64_256, 8, 2, 30), VR(F64_512, 4, 2, 5, 30), VR(F64_1024, 2, 2, 30), VR(F64_2048, 2, 1, 5),
     };
     return v;
