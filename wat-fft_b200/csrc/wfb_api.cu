@@ -593,9 +593,10 @@ wfb_plan *wfb_plan_create_ex(int kind, int precision, int layout, int n, long ba
     std::stable_sort(pl->variants.begin(), pl->variants.end(), [il](const Variant *a, const Variant *b) {
         return (il ? a->priority_il : a->priority) > (il ? b->priority_il : b->priority);
     });
-    if (pl->variants.size() > 8) {          // keep the 7 best plus the least-demanding (direct) fallback
+    if (pl->variants.size() > 8) {          // keep the 7 best plus the direct kernel (unaligned-pointer fallback, zero-copy path)
         const Variant *fallback = pl->variants.back();
         for (const Variant *v : pl->variants) if (v->align < fallback->align) fallback = v;
+        for (const Variant *v : pl->variants) if (v->direct && v->lanes == 1) { fallback = v; break; }
         pl->variants.resize(7);
         if (std::find(pl->variants.begin(), pl->variants.end(), fallback) == pl->variants.end()) pl->variants.push_back(fallback);
     }

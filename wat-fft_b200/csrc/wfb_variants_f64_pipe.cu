@@ -27,9 +27,13 @@ const std::vector<Variant> &variants_f64_pipe() {
         // 4096) and M = 2048 do not factor into two passes of <= 32 values per thread
         VRTS(D32_512, 2, 1, 62),
         // hoisted last-pass twiddles where the L1 data pipe is the bound (ncu r02: 84 % at r2c N = 2048, 78 % at 4096, 71 % at c2c 4096)
-        VTSH(F64_1024, 1, 2, 40), VTSH(F64_2048, 1, 2, 40), VTSH(F64_4096, 1, 1, 40),
+        // Measured (profiles/r02_sweep.md, burst clocks, fraction of the measured HBM peak, plain -> hoisted):
+        //   c2c N = 4096: 0.86 -> 0.875;  c2c N = 1024, 2048: 2-3 % SLOWER (not pipe-bound there)
+        //   r2c N = 2048: 0.81 -> 0.83, with 6 CTAs/SM (168-register cap) 0.87;  c2r N = 2048: 0.85 -> 0.90 -> 0.96
+        //   r2c N = 4096: 0.76 -> 0.78 (3 CTAs/SM: 0.78);  c2r N = 4096: 0.81 -> 0.79 -> 0.82;  r2c N = 1024 (32 values per thread): slower (spills)
+        VTSH(F64_1024, 1, 2, 40), VTSH(F64_2048, 1, 2, 40), VTSH(F64_4096, 1, 1, 62),
         VRTSH(D32_512, 2, 1, 40), VRTSH(F64_1024, 1, 2, 40), VRTSH(F64_2048, 1, 1, 40),
-        VRTSM(F64_1024, 1, 6, 39), VRTSHM(F64_1024, 1, 6, 39), VRTSM(F64_2048, 1, 3, 39), VRTSHM(F64_2048, 1, 3, 39), VRTSM(F64_512, 2, 8, 39),
+        VRTSM(F64_1024, 1, 6, 39), VRTSHM(F64_1024, 1, 6, 63), VRTSM(F64_2048, 1, 3, 39), VRTSHM(F64_2048, 1, 3, 63), VRTSM(F64_512, 2, 8, 39),
         VR(F64_128, 16, 2, 30), VR(F64_256, 8, 2, 30), VR(F64_512, 4, 2, 5, 30), VR(F64_1024, 2, 2, 30), VR(F64_2048, 2, 1, 5),
     };
     return v;
