@@ -79,6 +79,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        # nvidia-smi numbers the physical GPUs; a CUDA_VISIBLE_DEVICES list of plain indices maps the CUDA ordinal onto them
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if index < len(vis) and vis[index].isdigit():
+            index = int(vis[index])
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
         try:
@@ -312,7 +316,14 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # Rank -> GPU.  When the box shows more GPUs than there are ranks, the ranks take GPUs spread over the whole box
+    # (rank i -> GPU i * visible/world) instead of the first `world`: the host bridges of an 8-GPU board serve half the
+    # GPUs each, and on this pool GPUs 0..3 together get no more host bandwidth than GPU 0 alone
+    # (profiles/r02_pcie.md), which decides the end-to-end number.  WFB_BENCH_DEVICE_ORDER=seq restores rank i -> GPU i.
+    visible = torch.cuda.device_count()
+    spread = (os.environ.get("WFB_BENCH_DEVICE_ORDER", "spread") == "spread" and world > 1 and visible > world and visible % world == 0)
+    local = local_rank * (visible // world) if spread else local_rank
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -615,18 +626,31 @@ def run_ours(args):
         except Exception as ex:                                 # the tool is optional evidence, never a reason to fail the bench
             lat["native_c_abi"] = {"unavailable": repr(ex)}
 
-    # ---- pinned-copy ceiling of the host link, all ranks at once (the roofline of the e2e number)
-    gbs = (ctypes.c_double * 4)()
-    barrier()
-    C.check(lib.wfb_pcie_probe(local, 256 << 20, 8, gbs))
-    pcie_local = [float(x) for x in gbs]
-    if world > 1:
-        t = torch.tensor(pcie_local, device=dev, dtype=torch.float64)
-        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        pcie_min, pcie_sum = [float(x) for x in tmin], [float(x) for x in tsum]
-    else:
-        pcie_min, pcie_sum = pcie_local, pcie_local
+    # ---- pinned-copy ceiling of the host link (the roofline of the e2e number).  Every rank runs each phase -- H2D alone,
+    # D2H alone, both at once -- at the SAME moment: a barrier in front of every phase (round 1's probe let the ranks drift
+    # through the phases on their own and over-stated the multi-GPU ceiling).  Per phase and direction: the slowest rank's
+    # rate and the sum of the ranks' rates.  The e2e time is a max over ranks, so `world x slowest` is the ceiling it can reach.
+    probe = ctypes.c_void_p()
+    PROBE_BYTES, PROBE_ITERS = 256 << 20, 8
+    C.check(lib.wfb_pcie_probe_open(local, PROBE_BYTES, ctypes.byref(probe)))
+    sec = (ctypes.c_double * 2)()
+    pcie = {}
+    for name, dirs in (("alone_h2d", 1), ("alone_d2h", 2), ("duplex", 3)):
+        barrier()
+        C.check(lib.wfb_pcie_probe_run(probe, dirs, PROBE_ITERS, sec))
+        for bit, key, t in ((1, "h2d", sec[0]), (2, "d2h", sec[1])):
+            if not dirs & bit:
+                continue
+            rate = PROBE_ITERS * PROBE_BYTES / t / 1e9
+            if world > 1:
+                tt = torch.tensor([rate, -rate], device=dev, dtype=torch.float64)
+                tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+                tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                lo, total = -float(tmax[1]), float(tsum[0])
+            else:
+                lo = total = rate
+            pcie[("duplex_" if dirs == 3 else "alone_") + key] = {"slowest_rank": round(lo, 2), "sum": round(total, 2)}
+    lib.wfb_pcie_probe_close(probe)
     barrier()
 
     # ---- e2e: the headline workload through the public context API with pinned HOST buffers --------
@@ -717,8 +741,9 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
+    devices = {"visible": visible, "rank0_device": local, "order": "spread (rank i -> GPU i*visible/world)" if spread else "rank i -> GPU i"}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": warm,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": warm, "devices": devices,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(n_gpus),
         "achieved_GBs": agg_gbs,
@@ -729,13 +754,16 @@ def run_ours(args):
                 "parity": f"rows 0, 1, B/2, B-1 of every size checked against the oracle after forward() (worst = {worst:.3f} of the "
                           "2e-6*log2(N) bound) and against the input after inverse()",
                 "GBs_per_direction_per_gpu": round(e2e_dir_gbs, 2),
-                "pcie_peak_GBs": {"what": "plain cudaMemcpyAsync, 256 MiB pinned copies, CUDA-event timed, ALL ranks at the same time; "
-                                          "per GPU: minimum over ranks / sum over ranks",
-                                  "h2d_alone": [round(pcie_min[0], 2), round(pcie_sum[0], 2)], "d2h_alone": [round(pcie_min[1], 2), round(pcie_sum[1], 2)],
-                                  "h2d_duplex": [round(pcie_min[2], 2), round(pcie_sum[2], 2)], "d2h_duplex": [round(pcie_min[3], 2), round(pcie_sum[3], 2)]},
-                "frac": round(e2e_dir_gbs * n_gpus / max(1e-9, min(pcie_sum[2], pcie_sum[3])), 3),
-                "frac_note": "achieved bytes per direction / the slower direction of the concurrent duplex pinned-copy ceiling (sum over ranks); "
-                             "every transform crosses the link once each way, so this is the roofline of the e2e number",
+                "pcie_peak_GBs": dict({"what": f"plain cudaMemcpyAsync, {PROBE_ITERS} x {PROBE_BYTES >> 20} MiB pinned copies per direction, CUDA-event timed, "
+                                               "every rank in the same phase at the same time (barrier per phase); GB/s per direction: the slowest "
+                                               "rank's rate and the sum over the ranks"}, **pcie),
+                "frac": round(e2e_dir_gbs * n_gpus / max(1e-9, min(pcie["duplex_h2d"]["sum"], pcie["duplex_d2h"]["sum"])), 3),
+                "frac_of_slowest_rank_ceiling": round(e2e_dir_gbs / max(1e-9, min(pcie["duplex_h2d"]["slowest_rank"], pcie["duplex_d2h"]["slowest_rank"])), 3),
+                "frac_note": "achieved bytes per direction / the slower direction of the concurrent duplex pinned-copy ceiling: `frac` against the sum "
+                             "over ranks, `frac_of_slowest_rank_ceiling` against n_gpus x the slowest rank (the e2e time is a max over ranks, and the "
+                             "host fabric does not share its bandwidth evenly).  Every transform crosses the link once each way, so this is the "
+                             "roofline of the e2e number; tools/microbench/pcie_peak.cu measures the same ceiling from one C process "
+                             "(profiles/r02_pcie.md)",
                 "companions": comp},
         "gpu_launches": int(launches),
         "roofline": roofline,

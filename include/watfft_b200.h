@@ -145,13 +145,16 @@ WFB_API int wfb_plan_current_variant(wfb_plan *plan, int direction);
 /* Algorithmic bytes one exec moves (one read + one write of the payload; twiddles excluded). */
 WFB_API size_t wfb_plan_algorithmic_bytes(wfb_plan *plan);
 
-/* Staging knobs of wfb_exec (defaults from the environment: WFB_MAPPED_MAX_KB, WFB_STAGE_CHUNK_MB, WFB_STAGE_STREAMS).
+/* Staging knobs of wfb_exec (defaults from the environment: WFB_MAPPED_MAX_KB, WFB_STAGE_CHUNK_MB, WFB_STAGE_STREAMS,
+ * WFB_STAGE_RAMP).
  *   WFB_OPT_MAPPED_MAX_BYTES   payloads (input + output bytes) up to this size skip the copies: ONE kernel launch reads
  *                              and writes the pinned, device-mapped host buffers directly.  This is the path of the
  *                              reference's own call shape, batch = 1 (index.js:84-89).  0 disables it.
  *   WFB_OPT_STAGE_CHUNK_BYTES  bytes of the widest plane per chunk of the H2D / kernel / D2H pipeline
- *   WFB_OPT_STAGE_STREAMS      streams the chunks cycle over (1..6) */
-enum { WFB_OPT_MAPPED_MAX_BYTES = 0, WFB_OPT_STAGE_CHUNK_BYTES = 1, WFB_OPT_STAGE_STREAMS = 2 };
+ *   WFB_OPT_STAGE_STREAMS      streams the chunks cycle over (1..6)
+ *   WFB_OPT_STAGE_RAMP         1 (default): the pipeline starts and ends with short chunks (1/8, 1/4, 1/2 of the
+ *                              steady-state size), shortening the two copies that have nothing to overlap with */
+enum { WFB_OPT_MAPPED_MAX_BYTES = 0, WFB_OPT_STAGE_CHUNK_BYTES = 1, WFB_OPT_STAGE_STREAMS = 2, WFB_OPT_STAGE_RAMP = 3 };
 WFB_API int wfb_plan_set_option(wfb_plan *plan, int option, long value);
 WFB_API long wfb_plan_get_option(wfb_plan *plan, int option);
 /* Which path the latest wfb_exec took. */
@@ -162,6 +165,14 @@ WFB_API int wfb_plan_last_path(wfb_plan *plan);
  * D2H running at the same time (GB/s each; `bytes` per copy, `iters` copies per direction).  The denominator of the
  * end-to-end (host-buffer) throughput: wfb_exec cannot move a transform faster than its bytes cross this link. */
 WFB_API int wfb_pcie_probe(int device, size_t bytes, int iters, double gbs[4]);
+/* The same probe in phases, for callers that drive several GPUs (one process or thread each) and want every GPU in the
+ * same phase at the same moment -- open (allocates, one untimed copy each way), then per phase: barrier across the
+ * ranks, run.  directions: 1 = H2D, 2 = D2H, 3 = both at once; seconds[0] / seconds[1] = device time of the H2D / D2H
+ * train of `iters` copies of `bytes` (0 for a direction not run). */
+typedef struct wfb_pcie_probe_state wfb_pcie_probe_state;
+WFB_API int wfb_pcie_probe_open(int device, size_t bytes, wfb_pcie_probe_state **out);
+WFB_API int wfb_pcie_probe_run(wfb_pcie_probe_state *probe, int directions, int iters, double seconds[2]);
+WFB_API void wfb_pcie_probe_close(wfb_pcie_probe_state *probe);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 WFB_API unsigned long long wfb_kernel_launch_count(void);
 

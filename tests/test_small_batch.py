@@ -163,6 +163,68 @@ def test_pcie_probe(wf):
 
 
 @pytest.mark.gpu
+def test_pcie_probe_phases(wf):
+    """The phase-wise probe (what bench.py drives with a barrier across the ranks in front of every phase)."""
+    lib = wf._cabi.lib()
+    h = ctypes.c_void_p()
+    assert lib.wfb_pcie_probe_open(0, 32 << 20, ctypes.byref(h)) == 0
+    sec = (ctypes.c_double * 2)()
+    for directions in (1, 2, 3):
+        assert lib.wfb_pcie_probe_run(h, directions, 3, sec) == 0
+        for bit, t in ((1, sec[0]), (2, sec[1])):
+            if directions & bit:
+                assert 1.0 < 3 * (32 << 20) / t / 1e9 < 200.0, (directions, list(sec))
+            else:
+                assert t == 0.0
+    assert lib.wfb_pcie_probe_run(h, 0, 3, sec) != 0
+    lib.wfb_pcie_probe_close(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [2000, 2001, 1731])
+@pytest.mark.parametrize("ramp", [1, 0])
+def test_staging_pipeline_chunk_schedule(wf, oracle, batch, ramp):
+    """Every row of a pipelined wfb_exec is transformed exactly once whatever the chunk schedule: ramped ends (short first
+    and last chunks), the even-remainder chunk in the middle, an odd batch's last row; c2c split and the (n+2)-wide r2c rows."""
+    C = wf._cabi
+    n = 64
+    rng = np.random.default_rng(batch)
+    ctx = wf.createFFTf32Split(n, batch=batch)
+    ctx.plan.set_option(C.OPT_MAPPED_MAX_BYTES, 0)
+    ctx.plan.set_option(C.OPT_STAGE_CHUNK_BYTES, 32 << 10)      # 128 rows per chunk: ramp 16, 32, 64
+    ctx.plan.set_option(C.OPT_STAGE_RAMP, ramp)
+    assert ctx.plan.get_option(C.OPT_STAGE_RAMP) == ramp
+    re = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    im = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    ctx.getRealBuffer()[:] = re.ravel()
+    ctx.getImagBuffer()[:] = im.ravel()
+    ctx.forward()
+    assert ctx.plan.last_path() == C.PATH_PIPELINED
+    got = ctx.getRealBuffer().reshape(batch, n) + 1j * ctx.getImagBuffer().reshape(batch, n)
+    want = np.fft.fft(re.astype(np.float64) + 1j * im.astype(np.float64), axis=1)
+    assert np.max(np.abs(got - want)) / np.sqrt(2 * n) <= f32_bound(n)
+    o_re, o_im = oracle.fft_split_f32(re[-1], im[-1])
+    assert rel_err(np.r_[got[-1].real, got[-1].imag], np.r_[o_re, o_im], np.r_[re[-1], im[-1]]) <= f32_bound(n)
+    ctx.inverse()
+    assert np.max(np.abs(ctx.getRealBuffer().reshape(batch, n) - re)) < 1e-5
+    ctx.dispose()
+    r = wf.createRFFTf32(n, batch=batch)
+    r.plan.set_option(C.OPT_MAPPED_MAX_BYTES, 0)
+    r.plan.set_option(C.OPT_STAGE_CHUNK_BYTES, 32 << 10)
+    r.plan.set_option(C.OPT_STAGE_RAMP, ramp)
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    r.getInputBuffer()[:] = x.ravel()
+    r.forward()
+    assert r.plan.last_path() == C.PATH_PIPELINED
+    spec = r.getOutputBuffer().reshape(batch, n + 2)
+    want = np.fft.rfft(x.astype(np.float64), axis=1)
+    assert np.max(np.abs((spec[:, 0::2] + 1j * spec[:, 1::2]) - want)) / np.sqrt(n) <= f32_bound(n)
+    r.inverse()
+    assert np.max(np.abs(r.getInputBuffer().reshape(batch, n) - x)) < 1e-5
+    r.dispose()
+
+
+@pytest.mark.gpu
 def test_unused_second_plane_pointer_is_ignored(wf, oracle):
     """d_in[1]/d_out[1] are documented as unused for R2C and interleaved C2C; an odd or stale value there must
     neither demote the launch to the unaligned-pointer fallback nor fail."""

@@ -6,7 +6,11 @@
 //                hostalloc_wc     cudaHostAllocWriteCombined (H2D source only; no snooping of CPU caches)
 //                register_thp     aligned_alloc + madvise(MADV_HUGEPAGE) + first touch by the worker + cudaHostRegister
 //   affinity:    none | spread    (worker i pinned to the i-th slice of the allowed CPUs before it allocates)
-// Build: make -C tools/microbench pcie_peak      Run: tools/microbench/pcie_peak [MiB per copy = 256] [copies = 6]
+//   device order: seq     GPUs 0 .. G-1
+//                 spread  GPUs i * (all / G): on a two-root-complex host the first half of the GPUs hangs off one
+//                         complex and the second half off the other, so G < all GPUs in `seq` order share ONE complex
+// Build: make -C tools/microbench pcie_peak
+// Run:   tools/microbench/pcie_peak [MiB per copy = 256] [copies = 6] [orders = seq | spread | both | pairs] [alloc mode | all]
 #include <cuda_runtime.h>
 #include <pthread.h>
 #include <sched.h>
@@ -37,8 +41,8 @@ static void pin_slice(int i, int n) {
     pthread_setaffinity_np(pthread_self(), sizeof mine, &mine);
 }
 
-static void worker(int dev, int ngpu, const std::string &mode, bool spread, size_t bytes, int copies, Result *out) {
-    if (spread) pin_slice(dev, ngpu);
+static void worker(int slot, int dev, int ngpu, const std::string &mode, bool spread, size_t bytes, int copies, Result *out) {
+    if (spread) pin_slice(slot, ngpu);
     CK(cudaSetDevice(dev));
     void *h[2], *d[2];
     for (int i = 0; i < 2; i++) {
@@ -90,23 +94,44 @@ int main(int argc, char **argv) {
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     for (int d = 0; d < ndev; d++) { CK(cudaSetDevice(d)); CK(cudaFree(0)); }
+    const std::string orders = argc > 3 ? argv[3] : "seq";
+    const std::string only = argc > 4 ? argv[4] : "all";
     const char *modes[] = {"hostalloc", "hostalloc_wc", "register_thp"};
-    for (int g = 1; g <= ndev; g *= 2)
+    // device sets: seq / spread for G = 1, 2, 4, ...; `pairs` = {0, k} for every k (which GPUs share a host bridge with GPU 0?)
+    std::vector<std::vector<int>> sets;
+    if (orders == "pairs") {
+        for (int k = 1; k < ndev; k++) sets.push_back({0, k});
+    } else {
+        for (int order = 0; order < 2; order++)
+            for (int g = 1; g <= ndev; g *= 2) {
+                if ((order == 0 && orders == "spread") || (order == 1 && (orders == "seq" || g == 1 || g == ndev))) continue;
+                std::vector<int> v;
+                for (int d = 0; d < g; d++) v.push_back(order ? d * (ndev / g) : d);
+                sets.push_back(v);
+            }
+    }
+    for (const std::vector<int> &set : sets)
         for (const char *mode : modes)
             for (int spread = 0; spread < 2; spread++) {
+                const int g = (int)set.size();
                 if (spread && g == 1) continue;
+                if (only != "all" && only != mode) continue;
                 pthread_barrier_init(&g_bar, nullptr, g);
                 std::vector<Result> r(g);
                 std::vector<std::thread> th;
-                for (int d = 0; d < g; d++) th.emplace_back(worker, d, g, std::string(mode), spread != 0, bytes, copies, &r[d]);
+                std::string devs;
+                for (int d = 0; d < g; d++) {
+                    devs += (d ? "," : "") + std::to_string(set[d]);
+                    th.emplace_back(worker, d, set[d], g, std::string(mode), spread != 0, bytes, copies, &r[d]);
+                }
                 for (auto &t : th) t.join();
                 pthread_barrier_destroy(&g_bar);
                 auto agg = [&](double Result::*f, double *mn, double *sum) { *mn = 1e30; *sum = 0; for (auto &x : r) { *mn = std::min(*mn, x.*f); *sum += x.*f; } };
                 double a[8];
                 agg(&Result::h2d, &a[0], &a[1]); agg(&Result::d2h, &a[2], &a[3]); agg(&Result::dup_h2d, &a[4], &a[5]); agg(&Result::dup_d2h, &a[6], &a[7]);
-                printf("{\"gpus\": %d, \"alloc\": \"%s\", \"affinity\": \"%s\", \"MiB\": %zu, \"h2d_min\": %.2f, \"h2d_sum\": %.2f, \"d2h_min\": %.2f, \"d2h_sum\": %.2f, "
+                printf("{\"gpus\": %d, \"devices\": \"%s\", \"alloc\": \"%s\", \"affinity\": \"%s\", \"MiB\": %zu, \"h2d_min\": %.2f, \"h2d_sum\": %.2f, \"d2h_min\": %.2f, \"d2h_sum\": %.2f, "
                        "\"duplex_h2d_min\": %.2f, \"duplex_h2d_sum\": %.2f, \"duplex_d2h_min\": %.2f, \"duplex_d2h_sum\": %.2f}\n",
-                       g, mode, spread ? "spread" : "none", bytes >> 20, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+                       g, devs.c_str(), mode, spread ? "spread" : "none", bytes >> 20, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
                 fflush(stdout);
             }
     return 0;

@@ -22,7 +22,7 @@ FORWARD, INVERSE = 0, 1
 STAGE_H2D, STAGE_D2H, SYNC, EXEC_DEFAULT = 1, 2, 4, 7
 BUF_TIME, BUF_SPECTRUM = 0, 1
 PLAN_NO_HOST_BUFFERS, PLAN_NO_DEVICE_BUFFERS = 1, 2
-OPT_MAPPED_MAX_BYTES, OPT_STAGE_CHUNK_BYTES, OPT_STAGE_STREAMS = 0, 1, 2
+OPT_MAPPED_MAX_BYTES, OPT_STAGE_CHUNK_BYTES, OPT_STAGE_STREAMS, OPT_STAGE_RAMP = 0, 1, 2, 3
 PATH_NONE, PATH_STAGED, PATH_PIPELINED, PATH_MAPPED = 0, 1, 2, 3
 OK, ERR_NO_DEVICE, ERR_BAD_SIZE, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_ALLOC, ERR_CUDA, ERR_NO_HOST_BUFFERS = (
     0, -1, -2, -3, -4, -5, -6, -7)
@@ -61,6 +61,9 @@ SYMBOLS = {
     "wfb_plan_get_option": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_int]),
     "wfb_plan_last_path": (ctypes.c_int, [ctypes.c_void_p]),
     "wfb_pcie_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "wfb_pcie_probe_open": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+    "wfb_pcie_probe_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "wfb_pcie_probe_close": (None, [ctypes.c_void_p]),
     "wfb_kernel_launch_count": (ctypes.c_ulonglong, []),
     "wfb_reference_twiddles": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2),
     "wfb_stft_create": (ctypes.c_void_p, [ctypes.c_int] * 4 + [ctypes.c_long, ctypes.c_int, ctypes.c_float, ctypes.c_float,

@@ -276,6 +276,7 @@ struct wfb_plan {
     long mapped_max_bytes;             // zero-copy below this many payload bytes (in + out)
     long stage_chunk_bytes;            // staging pipeline: bytes of the widest plane per chunk
     int stage_streams;                 // ... and the number of streams the chunks cycle over
+    bool stage_ramp;                   // short chunks at both ends of the pipeline (see exec_impl)
     int last_path;                     // WFB_PATH_* of the latest wfb_exec
     // completion flag of the zero-copy path: the kernel's last act is a store of `token` to this word of mapped host
     // memory (after a system-scope fence behind its data stores); wfb_exec polls it instead of calling into the driver
@@ -513,6 +514,7 @@ static int plan_init(wfb_plan *pl) {
     pl->mapped_max_bytes = env_long("WFB_MAPPED_MAX_KB", 256) << 10;
     pl->stage_chunk_bytes = std::max(1L, env_long("WFB_STAGE_CHUNK_MB", 32)) << 20;
     pl->stage_streams = (int)std::min<long>(wfb_plan::NPIPE, std::max(1L, env_long("WFB_STAGE_STREAMS", 3)));
+    pl->stage_ramp = env_long("WFB_STAGE_RAMP", 1) != 0;
     // the zero-copy path launches the direct-load kernel (no TMA pipeline to fill, no tile counter): lowest alignment need
     pl->mapped_variant = -1;
     for (size_t i = 0; i < pl->variants.size(); i++)
@@ -669,6 +671,7 @@ int wfb_plan_set_option(wfb_plan *pl, int option, long value) {
         case WFB_OPT_MAPPED_MAX_BYTES: pl->mapped_max_bytes = value; return WFB_OK;
         case WFB_OPT_STAGE_CHUNK_BYTES: if (value < 4096) return WFB_ERR_BAD_ARG; pl->stage_chunk_bytes = value; return WFB_OK;
         case WFB_OPT_STAGE_STREAMS: if (value < 1 || value > wfb_plan::NPIPE) return WFB_ERR_BAD_ARG; pl->stage_streams = (int)value; return WFB_OK;
+        case WFB_OPT_STAGE_RAMP: pl->stage_ramp = value != 0; return WFB_OK;
         default: return WFB_ERR_BAD_ARG;
     }
 }
@@ -678,6 +681,7 @@ long wfb_plan_get_option(wfb_plan *pl, int option) {
         case WFB_OPT_MAPPED_MAX_BYTES: return pl->mapped_max_bytes;
         case WFB_OPT_STAGE_CHUNK_BYTES: return pl->stage_chunk_bytes;
         case WFB_OPT_STAGE_STREAMS: return pl->stage_streams;
+        case WFB_OPT_STAGE_RAMP: return pl->stage_ramp ? 1 : 0;
         default: return -1;
     }
 }
@@ -851,9 +855,29 @@ static int exec_impl(wfb_plan *pl, int direction, int flags, void *const hs_in[2
         // order the pipeline after whatever is already queued on the plan's stream
         CK(cudaEventRecord(pl->start_ev, pl->stream));
         for (int i = 0; i < nstreams; i++) CK(cudaStreamWaitEvent(pl->pipe[i], pl->start_ev, 0));
-        int c = 0;
-        for (long r0 = 0; r0 < pl->batch; r0 += chunk, c++) {
-            const long rows = (pl->batch - r0 < chunk) ? pl->batch - r0 : chunk;
+        // Chunk schedule.  The first H2D copy has no D2H running beside it and the last D2H no H2D: those two ends are
+        // the part of the call that cannot overlap, so the schedule ramps up through short chunks (1/8, 1/4, 1/2 of the
+        // steady-state size) and down again.  Every chunk but the last keeps the alignment rules above.
+        std::vector<long> sched;
+        {
+            auto aligned = [](long c) { if (c >= 512) c &= ~255L; else if (c >= 2) c &= ~1L; return c < 1 ? 1L : c; };
+            const long ramp[3] = {aligned(chunk / 8), aligned(chunk / 4), aligned(chunk / 2)};
+            const long ends = 2 * (ramp[0] + ramp[1] + ramp[2]);
+            if (pl->stage_ramp && chunk >= 16 && pl->batch >= ends + 2 * chunk) {
+                long mid = pl->batch - ends;
+                for (int i = 0; i < 3; i++) sched.push_back(ramp[i]);
+                for (; mid >= chunk; mid -= chunk) sched.push_back(chunk);
+                const long rem = mid >= 2 ? (mid & ~1L) : 0;      // an even remainder keeps the next chunk start aligned
+                if (rem) sched.push_back(rem);
+                for (int i = 2; i >= 0; i--) sched.push_back(ramp[i]);
+                sched.back() += mid - rem;                         // (an odd batch's last row)
+            } else {
+                for (long r0 = 0; r0 < pl->batch; r0 += chunk) sched.push_back(pl->batch - r0 < chunk ? pl->batch - r0 : chunk);
+            }
+        }
+        long r0 = 0;
+        for (size_t c = 0; c < sched.size(); r0 += sched[c], c++) {
+            const long rows = sched[c];
             cudaStream_t s = pl->pipe[c % nstreams];
             char *di[2] = {nullptr, nullptr}, *dout[2] = {nullptr, nullptr};
             for (int i = 0; i < 2; i++) {
@@ -937,52 +961,82 @@ extern "C" {
 // Pinned-copy ceiling of the link wfb_exec stages over: plain cudaMemcpyAsync between a pinned host buffer and the
 // device, each direction alone and both at once (one stream each), CUDA-event timed.  bench.py runs it on every rank
 // at the same moment, so the figure is the CONCURRENT ceiling of the box, the roofline of the e2e number.
-int wfb_pcie_probe(int device, size_t bytes, int iters, double gbs[4]) {
-    if (!gbs || bytes < 4096 || iters < 1) return WFB_ERR_BAD_ARG;
+struct wfb_pcie_probe_state {
+    int device; size_t bytes;
+    void *h[2], *d[2];
+    cudaStream_t st[2];
+    cudaEvent_t ev[4];
+};
+
+void wfb_pcie_probe_close(wfb_pcie_probe_state *ps) {
+    if (!ps) return;
+    cudaSetDevice(ps->device);
+    for (int i = 0; i < 2; i++) { if (ps->h[i]) cudaFreeHost(ps->h[i]); if (ps->d[i]) cudaFree(ps->d[i]); if (ps->st[i]) cudaStreamDestroy(ps->st[i]); }
+    for (int i = 0; i < 4; i++) if (ps->ev[i]) cudaEventDestroy(ps->ev[i]);
+    delete ps;
+}
+
+int wfb_pcie_probe_open(int device, size_t bytes, wfb_pcie_probe_state **out) {
+    if (!out || bytes < 4096) return WFB_ERR_BAD_ARG;
+    *out = nullptr;
     int rc = check_device(device);
     if (rc) return rc;
     CK(cudaSetDevice(device));
-    void *h[2] = {nullptr, nullptr}, *d[2] = {nullptr, nullptr};
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; i++) { if (h[i]) cudaFreeHost(h[i]); if (d[i]) cudaFree(d[i]); if (st[i]) cudaStreamDestroy(st[i]); }
-        for (int i = 0; i < 4; i++) if (ev[i]) cudaEventDestroy(ev[i]);
-    };
-#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call); } } while (0)
+    wfb_pcie_probe_state *ps = new wfb_pcie_probe_state();
+    memset(ps, 0, sizeof *ps);
+    ps->device = device; ps->bytes = bytes;
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { wfb_pcie_probe_close(ps); return cuda_fail(e_, #call); } } while (0)
     for (int i = 0; i < 2; i++) {
-        CKP(cudaHostAlloc(&h[i], bytes, cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(h[i], 0, bytes);
-        CKP(cudaMalloc(&d[i], bytes));
-        CKP(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        CKP(cudaHostAlloc(&ps->h[i], bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(ps->h[i], 0, bytes);
+        CKP(cudaMalloc(&ps->d[i], bytes));
+        CKP(cudaStreamCreateWithFlags(&ps->st[i], cudaStreamNonBlocking));
     }
-    for (int i = 0; i < 4; i++) CKP(cudaEventCreate(&ev[i]));
-    auto run = [&](bool up, bool down, double *t_up, double *t_down) -> cudaError_t {
-        cudaError_t e;
-        for (int w = 0; w < 2; w++) {            // w = 0: warm-up pass
-            if (up) if ((e = cudaEventRecord(ev[0], st[0]))) return e;
-            if (down) if ((e = cudaEventRecord(ev[2], st[1]))) return e;
-            for (int i = 0; i < (w ? iters : 1); i++) {
-                if (up) if ((e = cudaMemcpyAsync(d[0], h[0], bytes, cudaMemcpyHostToDevice, st[0]))) return e;
-                if (down) if ((e = cudaMemcpyAsync(h[1], d[1], bytes, cudaMemcpyDeviceToHost, st[1]))) return e;
-            }
-            if (up) if ((e = cudaEventRecord(ev[1], st[0]))) return e;
-            if (down) if ((e = cudaEventRecord(ev[3], st[1]))) return e;
-            if ((e = cudaStreamSynchronize(st[0])) || (e = cudaStreamSynchronize(st[1]))) return e;
-        }
-        float ms;
-        if (up) { if ((e = cudaEventElapsedTime(&ms, ev[0], ev[1]))) return e; *t_up = ms * 1e-3; }
-        if (down) { if ((e = cudaEventElapsedTime(&ms, ev[2], ev[3]))) return e; *t_down = ms * 1e-3; }
-        return cudaSuccess;
-    };
-    double tu = 0, td = 0, tdu = 0, tdd = 0, dummy = 0;
-    CKP(run(true, false, &tu, &dummy));
-    CKP(run(false, true, &dummy, &td));
-    CKP(run(true, true, &tdu, &tdd));
+    for (int i = 0; i < 4; i++) CKP(cudaEventCreate(&ps->ev[i]));
+    // one untimed copy each way: first-touch costs of the mappings stay out of the timed phases
+    CKP(cudaMemcpyAsync(ps->d[0], ps->h[0], bytes, cudaMemcpyHostToDevice, ps->st[0]));
+    CKP(cudaMemcpyAsync(ps->h[1], ps->d[1], bytes, cudaMemcpyDeviceToHost, ps->st[1]));
+    CKP(cudaStreamSynchronize(ps->st[0]));
+    CKP(cudaStreamSynchronize(ps->st[1]));
 #undef CKP
+    *out = ps;
+    return WFB_OK;
+}
+
+int wfb_pcie_probe_run(wfb_pcie_probe_state *ps, int directions, int iters, double seconds[2]) {
+    if (!ps || !seconds || iters < 1 || !(directions & 3)) return WFB_ERR_BAD_ARG;
+    const bool up = directions & 1, down = directions & 2;
+    CK(cudaSetDevice(ps->device));
+    if (up) CK(cudaEventRecord(ps->ev[0], ps->st[0]));
+    if (down) CK(cudaEventRecord(ps->ev[2], ps->st[1]));
+    for (int i = 0; i < iters; i++) {
+        if (up) CK(cudaMemcpyAsync(ps->d[0], ps->h[0], ps->bytes, cudaMemcpyHostToDevice, ps->st[0]));
+        if (down) CK(cudaMemcpyAsync(ps->h[1], ps->d[1], ps->bytes, cudaMemcpyDeviceToHost, ps->st[1]));
+    }
+    if (up) CK(cudaEventRecord(ps->ev[1], ps->st[0]));
+    if (down) CK(cudaEventRecord(ps->ev[3], ps->st[1]));
+    CK(cudaStreamSynchronize(ps->st[0]));
+    CK(cudaStreamSynchronize(ps->st[1]));
+    float ms;
+    seconds[0] = seconds[1] = 0.0;
+    if (up) { CK(cudaEventElapsedTime(&ms, ps->ev[0], ps->ev[1])); seconds[0] = ms * 1e-3; }
+    if (down) { CK(cudaEventElapsedTime(&ms, ps->ev[2], ps->ev[3])); seconds[1] = ms * 1e-3; }
+    return WFB_OK;
+}
+
+int wfb_pcie_probe(int device, size_t bytes, int iters, double gbs[4]) {
+    if (!gbs || bytes < 4096 || iters < 1) return WFB_ERR_BAD_ARG;
+    wfb_pcie_probe_state *ps = nullptr;
+    int rc = wfb_pcie_probe_open(device, bytes, &ps);
+    if (rc) return rc;
+    double a[2], b[2], c[2];
+    if ((rc = wfb_pcie_probe_run(ps, 1, iters, a)) || (rc = wfb_pcie_probe_run(ps, 2, iters, b)) || (rc = wfb_pcie_probe_run(ps, 3, iters, c))) {
+        wfb_pcie_probe_close(ps);
+        return rc;
+    }
     const double gb = (double)bytes * iters / 1e9;
-    gbs[0] = gb / tu; gbs[1] = gb / td; gbs[2] = gb / tdu; gbs[3] = gb / tdd;
-    cleanup();
+    gbs[0] = gb / a[0]; gbs[1] = gb / b[1]; gbs[2] = gb / c[0]; gbs[3] = gb / c[1];
+    wfb_pcie_probe_close(ps);
     return WFB_OK;
 }
 
