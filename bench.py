@@ -736,6 +736,56 @@ def run_ours(args):
                                           "h2d_bytes": n_gpus * ns * 4, "d2h_bytes": n_gpus * sp.numFrames * sp.numBins * 4}
         sp.dispose()
 
+    # ---- configs[4] end to end from ONE process: 262144 rows of N=4096 (8 GiB) in pinned host memory, cut into grains that
+    # the GPUs pull (watfft_b200.sharding.ShardedSplitFFT, schedule="dynamic"); rank 0 drives the very GPUs the ranks used,
+    # the other ranks wait at the barrier below with idle devices
+    sharded = None
+    if world > 1 and rank == 0 and not args.no_sharded_e2e:
+        try:
+            from watfft_b200.sharding import ShardedSplitFFT
+            step_dev = (visible // world) if spread else 1
+            devs = [i * step_dev for i in range(world)]
+            total, n4 = 262144, 4096
+            sh = ShardedSplitFFT(n4, total, devs, schedule="dynamic", grain_bytes=32 << 20, workers_per_device=2)
+            fill(sh.real.reshape(-1)); fill(sh.imag.reshape(-1)[::-1])
+            pick = sorted({0, 1, total // 2, total - 1})
+            keep = {r: (sh.real[r].copy(), sh.imag[r].copy()) for r in pick}
+            sh.run(); sh.run(inverse=True)                     # warm-up: contexts, tables, first touch
+            t0 = time.perf_counter(); sh.run(); t_f = time.perf_counter() - t0
+            counts = list(sh.last_counts)
+            for r in pick:
+                o_re, o_im = orc.fft_split_f32(*keep[r])
+                e = float(np.max(np.abs(np.r_[sh.real[r] - o_re, sh.imag[r] - o_im])) / np.linalg.norm(np.r_[keep[r][0], keep[r][1]]))
+                assert e <= 2e-6 * 12, f"sharded e2e parity row {r}: {e}"
+            t0 = time.perf_counter(); sh.run(inverse=True); t_i = time.perf_counter() - t0
+            for r in pick:
+                assert float(np.max(np.abs(sh.real[r] - keep[r][0]))) < 1e-3
+            nbytes = total * n4 * 8
+            sharded = {"workload": "configs[4]: c2c f32 split N=4096, 262144 rows (8 GiB) in pinned host memory, ONE process, the GPUs pull 32 MiB grains "
+                                   "(ShardedSplitFFT schedule=dynamic, 2 host threads per GPU), forward then inverse, in place",
+                       "devices": devs, "ms_forward": round(t_f * 1e3, 1), "ms_inverse": round(t_i * 1e3, 1),
+                       "Mtransforms_s": round(2 * total / (t_f + t_i) / 1e6, 2),
+                       "GBs_per_direction_total": round(2 * nbytes / (t_f + t_i) / 1e9, 2),
+                       "frac_of_duplex_sum": round(2 * nbytes / (t_f + t_i) / 1e9 / max(1e-9, min(pcie["duplex_h2d"]["sum"], pcie["duplex_d2h"]["sum"])), 3),
+                       "grains_per_device_forward": counts,
+                       "parity": "rows 0, 1, B/2, B-1 against the oracle after forward, against the input after inverse"}
+            sh.dispose()
+        except AssertionError:
+            raise
+        except Exception as ex:                             # an allocation failure here must not cost the run its headline
+            sharded = {"error": repr(ex)}
+    if world > 1 and not args.no_sharded_e2e:
+        # the other ranks wait on the rendezvous store (host side): an NCCL barrier would park a spinning kernel on the
+        # GPUs rank 0 is driving
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("wfb_sharded_done", "1")
+            else:
+                store.wait(["wfb_sharded_done"])
+        except Exception:
+            pass
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -773,6 +823,8 @@ def run_ours(args):
         "configs": configs,
         "latency": lat,
     }
+    if sharded:
+        line["e2e"]["one_process_sharded"] = sharded
     if n_gpus == 1 and not args.no_cpu_baseline:
         cpu = CpuReference()
         line["cpu_baseline"] = cpu.baseline_block(steps=5, warmup=1)
@@ -820,6 +872,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-e2e", action="store_true", help="skip the one-process configs[4] end-to-end leg (N > 1 only)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not (args.impl == "ours" and args.gpus > 1 and world == 1):      # (the torchrun re-launch prints through its ranks)

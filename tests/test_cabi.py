@@ -108,6 +108,27 @@ def test_twiddle_tables_match_reference_module_memory(wf, watref):
     assert np.array_equal(re, t[0::2]) and np.array_equal(im, t[1::2])
 
 
+def test_f64_rfft_table_mirror_symmetry(wf, watref):
+    """The f64 r2c kernels form T[M-k] from T[k] in registers (ld_tw_mirror in wfb_kernels.cuh) instead of loading the
+    reference's separately tabulated entry (fft_real_combined.wat:502-503,533-534).  That is sound because the reference's
+    range reduction makes the two entries mirror images to within one rounding -- checked here on the bytes the reference's
+    own precompute_rfft_twiddles writes, for every size, k = M/2 (which pairs with itself and keeps its entry) excluded."""
+    lib = wf._cabi.lib()
+    worst = 0.0
+    for n in [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]:
+        m = n // 2
+        re, im = np.zeros(m + 1), np.zeros(m + 1)
+        lib.wfb_reference_twiddles(2, n, m + 1, re.ctypes.data, im.ctypes.data)
+        if n <= 8192:                                          # (the module's 8 pages end where the N = 16384 table would)
+            watref.call("fft_real_combined", "precompute_rfft_twiddles", n)
+            t = watref.view("fft_real_combined", np.float64, 393216, 2 * (m + 1)).copy()
+            assert np.array_equal(re, t[0::2]) and np.array_equal(im, t[1::2]), n
+        k = np.arange(1, m)
+        k = k[k != m // 2]
+        worst = max(worst, float(np.max(np.abs(re[m - k] + re[k]))), float(np.max(np.abs(im[m - k] - im[k]))))
+    assert worst <= 4.5e-16, worst             # measured: 3.3e-16 (1.5 ulp of 1.0)
+
+
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under wat-fft_b200/ may reference it."""
     for p in (ROOT / "wat-fft_b200").rglob("*"):

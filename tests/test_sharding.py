@@ -66,3 +66,35 @@ def test_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("schedule", ["static", "dynamic"])
+def test_sharded_split_fft_one_process(wf, oracle, schedule):
+    """ShardedSplitFFT from one process over every visible device (a 1-GPU box shards over GPU 0 twice): every row is
+    transformed exactly once whichever device or worker took it, including the short last grain."""
+    import numpy as np
+    import torch
+    from conftest import f32_bound, rel_err
+    from watfft_b200.sharding import ShardedSplitFFT
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    n, batch = 256, 10007                                   # 1 KiB rows; 64 KiB grains -> 157 grains, the last one 23 rows
+    rng = np.random.default_rng(3)
+    re = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    im = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    sh = ShardedSplitFFT(n, batch, devices, schedule=schedule, grain_bytes=64 << 10, workers_per_device=2)
+    sh.scatter(re, im)
+    sh.run()
+    g_re, g_im = sh.gather()
+    want = np.fft.fft(re.astype(np.float64) + 1j * im.astype(np.float64), axis=1)
+    assert np.max(np.abs((g_re + 1j * g_im) - want)) / np.sqrt(2 * n) <= f32_bound(n)
+    for r in (0, batch // 2, batch - 1):
+        o_re, o_im = oracle.fft_split_f32(re[r], im[r])
+        assert rel_err(np.r_[g_re[r], g_im[r]], np.r_[o_re, o_im], np.r_[re[r], im[r]]) <= f32_bound(n)
+    if schedule == "dynamic":
+        assert sum(sh.last_counts) == len(sh.grains) == -(-batch // sh.grain)
+    sh.run(inverse=True)
+    b_re, b_im = sh.gather()
+    assert np.max(np.abs(b_re - re)) < 1e-5 and np.max(np.abs(b_im - im)) < 1e-5
+    sh.dispose()

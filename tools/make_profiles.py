@@ -233,6 +233,30 @@ def pcie():
                            f"{e['GBs_per_direction_per_gpu'] / min(g8['duplex_h2d_min'], g8['duplex_d2h_min']):.2f} of the slowest-GPU rate (the timing is a max over ranks).")
         except Exception as ex:
             out.append(f"(bench_n8.json unreadable: {ex!r})")
+    pairs = [json.loads(l) for f in ("pcie_pairs.jsonl", "pcie_spread.jsonl") if (G / f).exists() for l in open(G / f) if l.startswith("{")]
+    pairs = [r for r in pairs if r["affinity"] == "none"]
+    if pairs:
+        out += ["", "## Which GPUs share a host bridge (`pcie_peak 256 6 pairs` / `spread`, tools/pcie_diag2.sh)", "",
+                "| GPUs | H2D alone sum | D2H alone sum | duplex H2D sum | duplex D2H sum |", "|---|---|---|---|---|"]
+        seen = set()
+        for r in pairs:
+            if r["devices"] in seen:
+                continue
+            seen.add(r["devices"])
+            out.append(f"| {r['devices']} | {r['h2d_sum']} | {r['d2h_sum']} | {r['duplex_h2d_sum']} | {r['duplex_d2h_sum']} |")
+        out += ["", "GPU 0 paired with GPU 1, 2 or 3 gets the one-GPU duplex rate in total; paired with GPU 4..7 it gets 1.5-1.6 x: the board's",
+                "GPUs hang off two host bridges (0-3, 4-7), and each bridge's path to host memory carries about what one GPU can use.  Hence",
+                "`bench.py` places rank i on GPU i * visible/world when the box shows more GPUs than ranks (WFB_BENCH_DEVICE_ORDER=seq",
+                "restores rank i -> GPU i).  Four GPUs spread over both bridges reach 83 / 92 GB/s, eight 77 / 82: the box as a whole tops out there."]
+        for n in (2, 4):
+            f = G / f"bench_n{n}_spread.json"
+            if f.exists():
+                try:
+                    d = json.load(open(f)); e = d["e2e"]
+                    out.append(f"* `bench.py --gpus {n}` ({d['devices']['order']}): e2e {e['value'] / 1e6:.1f} M transforms/s, {e['GBs_per_direction_per_gpu']} GB/s per direction per GPU; "
+                               f"{e['frac']} of the duplex sum measured in that run, {e['frac_of_slowest_rank_ceiling']} of n x the slowest rank.")
+                except Exception as ex:
+                    out.append(f"* bench_n{n}_spread.json unreadable: {ex!r}")
     topo = G / "pcie_topology.txt"
     if topo.exists():
         out += ["", "## Box topology (`tools/pcie_diag.sh`)", "", "```", topo.read_text().strip(), "```"]

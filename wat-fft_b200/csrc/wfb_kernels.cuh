@@ -678,6 +678,25 @@ template <> struct RealPost<double> {
     }
 };
 
+// Second twiddle of a bin pair (k, M-k) in the f64 post-process.  The reference tabulates T[k] and T[M-k] separately
+// (fft_real_combined.wat:502-503,533-534), but its range reduction folds the angle of T[M-k] onto the argument of T[k]
+// (-PI - x for the sine, PI + x with sign -1 for the cosine, fft_combined.wat:43-106), so the two entries are mirror images:
+// T[M-k] = (-T[k].re, T[k].im) to within ONE rounding of the folded argument -- measured over every table N = 8..16384:
+// max |difference| = 3.3e-16 (tests/test_cabi.py::test_f64_rfft_table_mirror_symmetry), five orders below the
+// 6.5e-11 Taylor error both carry and 1e-3 of the parity bound.  Forming it in registers removes one 16-byte load per
+// bin pair: in the f64 r2c kernels those loads were as many bytes through the L1 data pipe as a whole pass over the data
+// (the c2r direction, which needs only T[k], ran 5-13 % faster for that reason).  k = M/2 pairs with itself and keeps its
+// own table entry (RealPost<double>::middle).  -DWFB_F64_MIRROR_TW=0 restores the second load.
+#ifndef WFB_F64_MIRROR_TW
+#define WFB_F64_MIRROR_TW 1
+#endif
+template <typename R>
+__device__ __forceinline__ twd<R> ld_tw_mirror(const typename RT<R>::twel *rtw, int k, int m, const twd<R> &w) {
+    if constexpr (sizeof(typename RT<R>::scalar) == 8 && WFB_F64_MIRROR_TW) return twd<R>{rneg(w.x), w.y, w.ny};
+    else if constexpr (sizeof(typename RT<R>::scalar) == 8) return ld_tw(rtw + (m - k));
+    else return w;                                     // f32: one twiddle serves both bins (RealPost<R>::pair)
+}
+
 template <typename R, class PL, int X, int PADQ, int MINB>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
@@ -725,7 +744,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_r2c(const __grid_constant__ 
             } else {
                 const cx<R> z = sm[pad_idx<PADQ>(k)], zm = sm[pad_idx<PADQ>(M - k)];
                 cx<R> xk, xm;
-                RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);
+                const twd<R> wk = ld_tw(rtw + k);
+                RealPost<R>::pair(z, zm, wk, ld_tw_mirror<R>(rtw, k, M, wk), xk, xm);
                 GIO<R>::st_il(out + k, rs, g.two, xk);
                 GIO<R>::st_il(out + (M - k), rs, g.two, xm);
             }
@@ -1542,7 +1562,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
                     } else {
                         const cx<R> zm = park[k];
                         cx<R> xk, xm;
-                        RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);
+                        const twd<R> wk = ld_tw(rtw + k);
+                RealPost<R>::pair(z, zm, wk, ld_tw_mirror<R>(rtw, k, M, wk), xk, xm);
                         put(out + k, xk);
                         put(out + (M - k), xm);
                     }
@@ -1886,7 +1907,8 @@ __global__ void __launch_bounds__(X, MINB) k_real_tpipe(const __grid_constant__ 
                 constexpr int k = k0 + 1;
                 const cx<R> z = x[slot_of_elem<PL, 0>(k)], zm = x[slot_of_elem<PL, 0>(M - k)];
                 cx<R> xk, xm;
-                RealPost<R>::pair(z, zm, ld_tw(rtw + k), ld_tw(rtw + (M - k)), xk, xm);     // (f32 ignores the second table entry)
+                const twd<R> wk = ld_tw(rtw + k);
+                RealPost<R>::pair(z, zm, wk, ld_tw_mirror<R>(rtw, k, M, wk), xk, xm);     // (f32 ignores the second entry)
                 put(k, xk);
                 put(M - k, xm);
             });

@@ -45,25 +45,65 @@ def max_over_ranks(value: float, backend_group=None) -> float:
 
 
 class ShardedSplitFFT:
-    """c2c f32 split-format transform of `batch` rows sharded over `devices` from one process."""
+    """c2c f32 split-format transform of `batch` rows sharded over `devices` from one process, host buffers in and out.
 
-    def __init__(self, size: int, batch: int, devices):
-        self.size, self.batch, self.devices = size, batch, list(devices)
+    schedule="static":  contiguous partition, one plan (with its own pinned host buffers) per device, launched back to back.
+    schedule="dynamic": ONE pinned host arena per plane for the whole batch; the rows are cut into grains and
+        `workers_per_device` host threads per device pull grains from a shared counter, each running
+        H2D -> kernel -> D2H for its grain on its own plan (wfb_exec_host).  The host fabric of a multi-GPU box does not
+        share its bandwidth evenly between GPUs (profiles/r02_pcie.md: the slowest of 8 GPUs gets 8.0 GB/s while the mean
+        is 9.7), so a static partition finishes with its slowest device; pulled grains finish together, at the SUM of the
+        devices' rates.  `last_counts` holds the grains each device processed in the latest run()."""
+
+    def __init__(self, size: int, batch: int, devices, schedule: str = "static", grain_bytes: int = 32 << 20,
+                 workers_per_device: int = 2):
+        if schedule not in ("static", "dynamic"):
+            raise ValueError("schedule must be 'static' or 'dynamic'")
+        self.size, self.batch, self.devices, self.schedule = size, batch, list(devices), schedule
         self.bounds = partition(batch, len(self.devices))
-        self.plans = [Plan(C.C2C, C.F32, C.SPLIT, size, e - b, d) if e > b else None
-                      for (b, e), d in zip(self.bounds, self.devices)]
+        self.last_counts = [0] * len(self.devices)
+        if schedule == "static":
+            self.plans = [Plan(C.C2C, C.F32, C.SPLIT, size, e - b, d) if e > b else None
+                          for (b, e), d in zip(self.bounds, self.devices)]
+            return
+        from .contexts import HostMemory
+        row = 4 * size
+        self._mem = [HostMemory(max(1, batch) * row), HostMemory(max(1, batch) * row)]
+        self.real = self._mem[0].view(np.float32, 0, batch * size).reshape(batch, size)
+        self.imag = self._mem[1].view(np.float32, 0, batch * size).reshape(batch, size)
+        g = max(1, grain_bytes // row)
+        if g >= 512:
+            g &= ~255                                  # whole kernel tiles per grain
+        self.grain = g
+        self.grains = [(r0, min(g, batch - r0)) for r0 in range(0, batch, g)]
+        flags = C.PLAN_NO_HOST_BUFFERS
+        self.workers = []                              # (device slot, plan for full grains)
+        for slot, d in enumerate(self.devices):
+            for _ in range(max(1, workers_per_device)):
+                self.workers.append((slot, Plan(C.C2C, C.F32, C.SPLIT, size, min(g, max(1, batch)), d, flags)))
+        self.plans = [w[1] for w in self.workers]
+        for pl in self.plans:
+            pl.set_option(C.OPT_MAPPED_MAX_BYTES, 0)   # grains are large: always the copy path
 
     def buffers(self, rank):
+        if self.schedule == "dynamic":
+            b, e = self.bounds[rank]
+            return self.real[b:e], self.imag[b:e]
         p = self.plans[rank]
         return p.host(0).reshape(-1, self.size), p.host(1).reshape(-1, self.size)
 
     def scatter(self, re: np.ndarray, im: np.ndarray):
+        if self.schedule == "dynamic":
+            self.real[:], self.imag[:] = re, im
+            return
         for r, (b, e) in enumerate(self.bounds):
             if self.plans[r] is not None:
                 hr, hi = self.buffers(r)
                 hr[:], hi[:] = re[b:e], im[b:e]
 
     def gather(self):
+        if self.schedule == "dynamic":
+            return self.real.copy(), self.imag.copy()
         re = np.empty((self.batch, self.size), np.float32)
         im = np.empty_like(re)
         for r, (b, e) in enumerate(self.bounds):
@@ -74,6 +114,8 @@ class ShardedSplitFFT:
 
     def run(self, inverse=False):
         d = C.INVERSE if inverse else C.FORWARD
+        if self.schedule == "dynamic":
+            return self._run_dynamic(d)
         for p in self.plans:            # asynchronous: all devices work concurrently
             if p is not None:
                 p.exec(d, C.STAGE_H2D | C.STAGE_D2H)
@@ -81,7 +123,54 @@ class ShardedSplitFFT:
             if p is not None:
                 p.sync()
 
+    def _run_dynamic(self, direction):
+        import threading
+        lock = threading.Lock()
+        state = {"next": 0}
+        counts = [0] * len(self.devices)
+        errors = []
+        row = 4 * self.size
+        base = (self._mem[0].ptr, self._mem[1].ptr)
+
+        def work(slot, plan):
+            tail = None
+            try:
+                while True:
+                    with lock:                          # claim the next grain (and count it for this device)
+                        i = state["next"]
+                        if i >= len(self.grains) or errors:
+                            break
+                        state["next"] = i + 1
+                        counts[slot] += 1
+                    r0, rows = self.grains[i]
+                    pl = plan
+                    if rows != plan.batch:             # the batch's last, shorter grain: a plan of its own size
+                        tail = pl = Plan(C.C2C, C.F32, C.SPLIT, self.size, rows, plan.device, C.PLAN_NO_HOST_BUFFERS)
+                        pl.set_option(C.OPT_MAPPED_MAX_BYTES, 0)
+                    ptrs = (base[0] + r0 * row, base[1] + r0 * row)
+                    pl.exec_host(direction, ptrs, ptrs, C.SYNC)      # in place, like the contexts; the GIL is released inside
+            except Exception as ex:                     # surfaced by run(): a worker must not die silently
+                errors.append(ex)
+            finally:
+                if tail is not None:
+                    tail.destroy()
+
+        threads = [threading.Thread(target=work, args=w) for w in self.workers]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        self.last_counts = counts
+        if errors:
+            raise errors[0]
+
     def dispose(self):
         for p in self.plans:
             if p is not None:
                 p.destroy()
+        self.plans = []
+        if self.schedule == "dynamic":
+            self.real = self.imag = None
+            for m in self._mem:
+                m.free()
+            self._mem = []
