@@ -412,7 +412,12 @@ def spectrogram_reference(samples, fft_size, hop, window_type="hann", zero_paddi
     """generateSpectrogram, spectrogram.js:281-360: per frame slice -> applyWindow (:27-38, product
     rounded to f32) -> zeroPad (:40-45) -> real FFT -> computeMagnitude (:47-58, rounded to f32) ->
     magnitudeToDb (:60-62) -> gain/range normalisation with the first 3 bins zeroed (:335-352).
-    `rfft` is the f32 real transform (n reals -> n+2 interleaved floats)."""
+    `rfft` is the f32 real transform (n reals -> n+2 interleaved floats).
+
+    PARITY UNPINNED for everything but the transform: the reference loop is JavaScript and no JS engine exists in this
+    image, so this restatement has no reference-run output behind it.  The r2c core it calls IS pinned (bit-identical to
+    the transpiled reference module, tests/test_oracle_pinning.py); window / magnitude / dB / normalise are restated from
+    the cited lines."""
     samples = np.asarray(samples, np.float32)
     wsize = fft_size // zero_padding
     bins = fft_size // 2 + 1

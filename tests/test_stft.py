@@ -1,5 +1,9 @@
 """Batched STFT front-end: the reference's spectrogram loop
-(playground/src/spectrogram.js:281-360) restated in oracle/oracle.py and fused into one kernel."""
+(playground/src/spectrogram.js:281-360) restated in oracle/oracle.py and fused into one kernel.
+
+Parity status: the r2c core of the oracle is pinned (bit-identical to the transpiled reference module); the window /
+magnitude / dB / normalise stage is a restatement with no reference-run output behind it (the reference loop is
+JavaScript; no JS engine in this image) -- PARITY UNPINNED for that stage."""
 import numpy as np
 import pytest
 
