@@ -322,8 +322,9 @@ def run_ours(args):
     # GPUs each, and on this pool GPUs 0..3 together get no more host bandwidth than GPU 0 alone
     # (profiles/r02_pcie.md), which decides the end-to-end number.  WFB_BENCH_DEVICE_ORDER=seq restores rank i -> GPU i.
     visible = torch.cuda.device_count()
-    spread = (os.environ.get("WFB_BENCH_DEVICE_ORDER", "spread") == "spread" and world > 1 and visible > world and visible % world == 0)
-    local = local_rank * (visible // world) if spread else local_rank
+    from watfft_b200.sharding import rank_device
+    local = rank_device(local_rank, world, visible, os.environ.get("WFB_BENCH_DEVICE_ORDER", "spread"))
+    spread = rank_device(world - 1, world, visible, os.environ.get("WFB_BENCH_DEVICE_ORDER", "spread")) != world - 1
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -743,8 +744,7 @@ def run_ours(args):
     if world > 1 and rank == 0 and not args.no_sharded_e2e:
         try:
             from watfft_b200.sharding import ShardedSplitFFT
-            step_dev = (visible // world) if spread else 1
-            devs = [i * step_dev for i in range(world)]
+            devs = [rank_device(i, world, visible, os.environ.get("WFB_BENCH_DEVICE_ORDER", "spread")) for i in range(world)]
             total, n4 = 262144, 4096
             sh = ShardedSplitFFT(n4, total, devs, schedule="dynamic", grain_bytes=32 << 20, workers_per_device=2)
             fill(sh.real.reshape(-1)); fill(sh.imag.reshape(-1)[::-1])

@@ -27,6 +27,21 @@ def test_partition_covers_rows(wf):
         partition(8, 0)
 
 
+def test_rank_device_orders(wf):
+    from watfft_b200.sharding import rank_device
+    assert [rank_device(i, 2, 8) for i in range(2)] == [0, 4]            # one rank per host bridge
+    assert [rank_device(i, 4, 8) for i in range(4)] == [0, 2, 4, 6]
+    assert [rank_device(i, 8, 8) for i in range(8)] == list(range(8))
+    assert [rank_device(i, 2, 2) for i in range(2)] == [0, 1]            # CUDA_VISIBLE_DEVICES already narrowed the box
+    assert [rank_device(i, 3, 8) for i in range(3)] == [0, 1, 2]         # no even spread: sequential
+    assert [rank_device(i, 2, 8, "seq") for i in range(2)] == [0, 1]
+    assert rank_device(0, 1, 8) == 0
+    for w in (2, 4, 8):                                                  # distinct GPUs whatever the order
+        assert len({rank_device(i, w, 8) for i in range(w)}) == w
+    with pytest.raises(ValueError):
+        rank_device(2, 2, 8)
+
+
 def test_world_size_2_gloo(tmp_path):
     script = tmp_path / "rank.py"
     script.write_text(textwrap.dedent(f"""

@@ -32,6 +32,18 @@ def partition(batch: int, world: int, rank: int | None = None):
     return bounds if rank is None else bounds[rank]
 
 
+def rank_device(local_rank: int, world: int, visible: int, order: str = "spread") -> int:
+    """GPU ordinal for a rank of a one-node job.  "spread": when the node shows more GPUs than there are ranks (and a
+    multiple of them), rank i takes GPU i * visible / world, so the ranks sit on different host bridges of the board --
+    on this pool GPUs 0-3 share one bridge and get no more host bandwidth together than one GPU alone
+    (profiles/r02_pcie.md).  "seq" (and every other case): rank i -> GPU i."""
+    if not 0 <= local_rank < world:
+        raise ValueError("local_rank outside the world")
+    if order == "spread" and world > 1 and visible > world and visible % world == 0:
+        return local_rank * (visible // world)
+    return local_rank
+
+
 def max_over_ranks(value: float, backend_group=None) -> float:
     """Timing reduction used by bench.py: the job time is the slowest rank's time."""
     import torch
