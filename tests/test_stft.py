@@ -111,7 +111,7 @@ def test_gpu_spectrogram_errors_and_long_signal(wf, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_fft,zp", [(256, 1), (512, 1), (1024, 1), (1024, 2), (2048, 1), (4096, 1), (4096, 4), (8192, 1)])
+@pytest.mark.parametrize("n_fft,zp", [(256, 1), (256, 2), (512, 1), (512, 2), (1024, 1), (1024, 2), (2048, 1), (4096, 1), (4096, 4), (8192, 1)])
 def test_span_kernel_many_tiles(wf, oracle, monkeypatch, n_fft, zp):
     """The span-staged persistent kernel with enough frames that every CTA loops over several tiles and the last tile is
     ragged: sampled frames against the reference loop, the whole picture against the direct kernel (different core plan,
@@ -138,8 +138,9 @@ def test_span_kernel_many_tiles(wf, oracle, monkeypatch, n_fft, zp):
 
 
 @pytest.mark.gpu
-def test_span_kernel_complex_output(wf, oracle, monkeypatch):
-    n_fft, hop = 1024, 256
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+def test_span_kernel_complex_output(wf, oracle, monkeypatch, n_fft):
+    hop = n_fft // 4
     ns = 4000 * hop + n_fft
     x = _signal(ns, seed=5)
     monkeypatch.setenv("WFB_STFT_SPAN", "1")
