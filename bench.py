@@ -485,6 +485,7 @@ def run_ours(args):
                 "frac": round(nbytes / ms / 1e6 / peak, 3), unit_name: round(units / ms / 1e3, 2)}
 
     configs = {}
+    r2c_rate = {}
     A1, B1 = (a_ptr, None), (b_ptr, None)
     rows_ = []
     for n in REAL_SIZES:                                      # configs[2]: rfft_split / irfft_split, B = 2^30/(4N)
@@ -493,6 +494,7 @@ def run_ours(args):
         nb = p.algorithmic_bytes()
         ms = time_launch(lambda: p.exec_device(C.FORWARD, A1, B1, sptr))
         rows_.append(row(f"r2c<f32,N={n}>", n, ms, nb, b, p.current_variant(0)))
+        r2c_rate[n] = rows_[-1]["Mtransforms_s"]
         ms = time_launch(lambda: p.exec_device(C.INVERSE, B1, A1, sptr))
         rows_.append(row(f"c2r<f32,N={n}>", n, ms, nb, b, p.current_variant(1)))
         p.destroy()
@@ -533,6 +535,12 @@ def run_ours(args):
         nb = sp.algorithmic_bytes()
         ms = time_launch(lambda: sp.run_device(a_ptr, b_ptr, sptr))
         r = row(f"stft<f32,N={n},hop=N/4,hann,dB>", n, ms, nb, sp.numFrames, "fused", "Mframes_s")
+        # the spectrogram's HBM bytes are a third of its r2c work (frames overlap 4x, half the bins' bytes leave): its
+        # yardstick is the plain r2c kernel's rows/s at the same N, measured a few lines up
+        plain = r2c_rate.get(n)
+        if plain:
+            r["r2c_Mrows_s"] = plain
+            r["frames_per_r2c_row"] = round(r["Mframes_s"] / plain, 3)
         rows_.append(r)
         sp.dispose()
     configs["STFT front-end (playground/src/spectrogram.js loop fused), 2^26 samples, hop N/4"] = rows_
