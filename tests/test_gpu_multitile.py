@@ -73,6 +73,60 @@ def test_c2c_f32_many_tiles(wf, oracle, n, layout):
     plan.destroy()
 
 
+
+@pytest.mark.parametrize("layout", ["split", "interleaved"])
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_c2c_f32_register_prefetch_many_tiles(wf, oracle, n, layout):
+    """The register-prefetch persistent kernels (k_c2c_rpf: the next transform is loaded into a second register set while
+    the current one is computed; results leave through two alternating shared-memory tiles): many tiles per CTA, an odd
+    tile count, both directions.  Same plan and twiddles as the default kernel, so the whole batch must match it BITWISE;
+    sampled rows against the oracle; repeated launches identical."""
+    torch, dev = _torch()
+    C = wf._cabi
+    batch = TARGET_BYTES // (8 * n) + 3
+    g = torch.Generator(device=dev); g.manual_seed(4000 + n)
+    flags = C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS
+    split = layout == "split"
+    a0 = torch.rand(batch * n * (1 if split else 2), device=dev, generator=g) * 2 - 1
+    a1 = torch.rand(batch * n, device=dev, generator=g) * 2 - 1 if split else None
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    plan = wf.Plan(C.C2C, C.F32, C.SPLIT if split else C.INTERLEAVED, n, batch, 0, flags)
+    names = plan.variants()
+    rpf = [i for i, v in enumerate(names) if "_rpf" in v]
+    assert rpf, names
+    for direction in (C.FORWARD, C.INVERSE):
+        ref0, ref1 = torch.empty_like(a0), (torch.empty_like(a1) if split else None)
+        plan.set_variant(0)
+        plan.exec_device(direction, (ptr(a0), ptr(a1)), (ptr(ref0), ptr(ref1)))
+        plan.sync()
+        for vi in rpf:
+            plan.set_variant(vi)
+            o0, o1 = torch.empty_like(a0), (torch.empty_like(a1) if split else None)
+            for rep in range(3):
+                o0.zero_()
+                plan.exec_device(direction, (ptr(a0), ptr(a1)), (ptr(o0), ptr(o1)))
+                plan.sync()
+                assert torch.equal(o0, ref0) and (not split or torch.equal(o1, ref1)), (names[vi], direction, rep)
+        if direction == C.FORWARD:
+            for r in _rows(batch, n)[:24]:
+                if split:
+                    x, y = a0[r * n:(r + 1) * n].cpu().numpy(), a1[r * n:(r + 1) * n].cpu().numpy()
+                    er, ei = oracle.fft_split_f32(x, y)
+                    got = np.r_[o0[r * n:(r + 1) * n].cpu().numpy(), o1[r * n:(r + 1) * n].cpu().numpy()]
+                    assert rel_err(got, np.r_[er, ei], np.r_[x, y]) <= f32_bound(n), (n, r)
+                else:
+                    z = a0[2 * r * n:2 * (r + 1) * n].cpu().numpy()
+                    assert rel_err(o0[2 * r * n:2 * (r + 1) * n].cpu().numpy(), oracle.fft_interleaved_f32(z), z) <= f32_bound(n), (n, r)
+    # in place (the contexts' call shape): the loads of the NEXT row are in flight while this row's results are stored
+    plan.set_variant(rpf[0])
+    b0, b1 = a0.clone(), (a1.clone() if split else None)
+    plan.exec_device(C.FORWARD, (ptr(b0), ptr(b1)), (ptr(b0), ptr(b1)))
+    plan.exec_device(C.INVERSE, (ptr(b0), ptr(b1)), (ptr(b0), ptr(b1)))
+    plan.sync()
+    assert float((b0 - a0).abs().max()) < 1e-4
+    plan.destroy()
+
+
 @pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
 def test_real_f32_many_tiles(wf, oracle, n):
     torch, dev = _torch()

@@ -1217,6 +1217,135 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
 
 
 // ----------------------------------------------------------------------------------------
+// Register-prefetch persistent c2c (large N, scalar lanes, one transform per CTA iteration).
+// ncu on the TMA-pipelined kernels above (profiles/r02_ncu_full.md) shows the shared-memory SRAM as their co-critical
+// unit, and 15-20 % of its wavefronts are LSU accesses replayed because the copy engine was using the banks: a
+// three-pass transform costs EIGHT passes over its tile there (bulk copy in, LDS, two exchanges, STS, bulk copy out).
+// This kernel takes the input off that SRAM: every thread loads the NEXT transform's E values straight from global
+// memory into a second register set (coalesced 128-byte LDGs, issued before the current transform's first pass and
+// consumed a whole transform later, so their latency is covered without a stage buffer), and the current transform
+// runs out of the first set.  The loop body is instantiated twice with the two register sets swapped (no copies).
+// TS: results leave through one of two alternating shared-memory tiles as bulk stores (as in k_c2c_pipe); otherwise
+// as per-thread streaming stores.
+// ----------------------------------------------------------------------------------------
+template <int N_> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_) : "memory"); }
+
+template <typename R, class PL, int PADQ, int IO, bool INV, int MINB, bool TS>
+__global__ void __launch_bounds__(PL::T, MINB) k_c2c_rpf(const __grid_constant__ KParams p) {
+    static_assert(PL::valid() && RT<R>::LANES == 1 && PL::T >= 32 && PL::npass() > 1, "multi-pass scalar-lane plans");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using S = typename VecOf<R>::s;
+    using V2 = typename VecOf<R>::v2;
+    constexpr int N = PL::N, T = PL::T, E = PL::E;
+    constexpr int LAST = PL::npass() - 1;
+    constexpr size_t BUF = pipe_buf_bytes<R, PL, PADQ, 1>();
+    constexpr int NBUF = TS ? 2 : 1;
+    long *slot = reinterpret_cast<long *>(smem_raw + NBUF * BUF);        // tile claimed for iteration parity 0 / 1
+    const int tid = threadIdx.x;
+    const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
+    const long tiles = p.batch;
+    const auto tw0 = UTw<R, PL>::make(p, tw);
+    const R sc = RT<R>::splat((S)p.scale);
+
+    auto load = [&](long row, cx<R> (&v)[E]) {
+        if constexpr (IO == IO_SPLIT) {
+            const S *re = reinterpret_cast<const S *>(p.in0) + row * N + tid;
+            const S *im = reinterpret_cast<const S *>(p.in1) + row * N + tid;
+            static_for<E>([&](auto E_) { CIDX(e, E_); v[e] = mk<R>(ld_stream(re + e * T), ld_stream(im + e * T)); });
+        } else {
+            const V2 *z = reinterpret_cast<const V2 *>(p.in0) + row * N + tid;
+            static_for<E>([&](auto E_) { CIDX(e, E_); const V2 a = ld_stream(z + e * T); v[e] = mk<R>(a.x, a.y); });
+        }
+    };
+    auto store_tile = [&](long row, int st) {                              // thread 0: the finished tile in buffer st
+        const unsigned char *src = smem_raw + st * BUF;
+        constexpr uint32_t ROWB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * N * sizeof(S));
+        tma_store_1d(reinterpret_cast<unsigned char *>(p.out0) + row * ROWB, src, ROWB);
+        if constexpr (IO == IO_SPLIT) tma_store_1d(reinterpret_cast<unsigned char *>(p.out1) + row * ROWB, src + ROWB, ROWB);
+        bulk_commit();
+    };
+
+    if (tid == 0) slot[0] = (long)atomicAdd(p.ctr, 1ULL);
+    __syncthreads();
+    long tile = slot[0], prev = -1;
+    int it = 0;
+    cx<R> ra[E], rb[E];
+    if (tile < tiles) load(tile, ra);
+
+    // one iteration: x holds `tile` (loads possibly still in flight), nx receives the next tile
+    auto iter = [&](cx<R> (&x)[E], cx<R> (&nx)[E]) -> bool {
+        const int st = TS ? (it & 1) : 0;
+        if (tid == 0) {
+            slot[(it + 1) & 1] = (long)atomicAdd(p.ctr, 1ULL);
+            // TS: the store issued one iteration ago (tile it-2, out of buffer st) has had a whole transform to drain
+            if constexpr (TS) bulk_wait_read<0>();
+        }
+        if constexpr (TS) fence_proxy_async();        // our result writes (generic proxy) precede the bulk store below
+        __syncthreads();                              // slot published; last tile's results complete; scratch free
+        if constexpr (TS) { if (prev >= 0 && tid == 0) store_tile(prev, st ^ 1); }
+        if (tile >= tiles) return false;
+        const long next = slot[(it + 1) & 1];
+        if (next < tiles) load(next, nx);
+        unsigned char *buf = smem_raw + st * BUF;
+        run_all<R, PL, PADQ, 1, INV>(x, tw, tw0, reinterpret_cast<cx<R> *>(buf), tid, 0, false);
+        if constexpr (TS) {
+            __syncthreads();                          // the result rows alias the scratch everyone just read
+            if constexpr (IO == IO_SPLIT) {
+                S *re = reinterpret_cast<S *>(buf) + tid;
+                S *im = re + N;
+                static_for<E>([&](auto S_) {
+                    CIDX(slot_, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot_);
+                    cx<R> v = x[slot_];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    re[e * T] = v.x; im[e * T] = v.y;
+                });
+            } else {
+                V2 *z = reinterpret_cast<V2 *>(buf) + tid;
+                static_for<E>([&](auto S_) {
+                    CIDX(slot_, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot_);
+                    cx<R> v = x[slot_];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    V2 o; o.x = v.x; o.y = v.y;
+                    z[e * T] = o;
+                });
+            }
+        } else {
+            if constexpr (IO == IO_SPLIT) {
+                S *re = reinterpret_cast<S *>(p.out0) + tile * N + tid;
+                S *im = reinterpret_cast<S *>(p.out1) + tile * N + tid;
+                static_for<E>([&](auto S_) {
+                    CIDX(slot_, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot_);
+                    cx<R> v = x[slot_];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    GIO<R>::st_split(re + e * T, im + e * T, 0, false, v);
+                });
+            } else {
+                V2 *z = reinterpret_cast<V2 *>(p.out0) + tile * N + tid;
+                static_for<E>([&](auto S_) {
+                    CIDX(slot_, S_);
+                    constexpr int e = out_elem<PL, LAST>(slot_);
+                    cx<R> v = x[slot_];
+                    if (INV) v = mk<R>(rmul(v.x, sc), rmul(v.y, sc));
+                    GIO<R>::st_il(z + e * T, 0, false, v);
+                });
+            }
+        }
+        prev = tile; tile = next; it++;
+        return true;
+    };
+    for (;;) {
+        if (!iter(ra, rb)) break;
+        if (!iter(rb, ra)) break;
+    }
+    if constexpr (TS) { if (tid == 0) bulk_wait_read<0>(); }             // shared memory must outlive the stores that read it
+    claim_epilogue(p.ctr);
+}
+
+
+// ----------------------------------------------------------------------------------------
 // Persistent, fully TMA-fed thread-per-row c2c (N <= 64, f32).  Same arithmetic as k_c2c_tile, but no thread
 // ever touches global memory: rows arrive by bulk copy, are transformed in place by their thread, and leave by
 // bulk store.  Against k_c2c_tile this drops the cooperative staging loops -- a third of the LSU instructions

@@ -96,6 +96,23 @@ template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ,
     }
 };
 
+// register-prefetch persistent c2c (k_c2c_rpf): one transform per CTA iteration
+template <typename R, class PL, int MINB, bool TS, int PQ = PADQ> struct RegPipeLaunchers {
+    static constexpr size_t smem = (TS ? 2 : 1) * pipe_buf_bytes<R, PL, PQ, 1>() + 64;
+    static cudaError_t c2c(int io, int dir, const KParams &p, long batch, cudaStream_t s) {
+        const void *k;
+        if (io == IO_SPLIT)
+            k = dir ? (const void *)k_c2c_rpf<R, PL, PQ, IO_SPLIT, true, MINB, TS> : (const void *)k_c2c_rpf<R, PL, PQ, IO_SPLIT, false, MINB, TS>;
+        else
+            k = dir ? (const void *)k_c2c_rpf<R, PL, PQ, IO_INTERLEAVED, true, MINB, TS> : (const void *)k_c2c_rpf<R, PL, PQ, IO_INTERLEAVED, false, MINB, TS>;
+        return launch_persistent(k, smem, PL::T, batch, p, s);
+    }
+    static Variant make(const char *name, int priority, int priority_inv = -1, int priority_il = -1) {
+        // TS: bulk stores need 16-byte aligned rows; the loads are plain element loads either way
+        return Variant{name, PL::N, PL::T, 1, smem, 1, priority, priority_inv < 0 ? priority : priority_inv, priority_il < 0 ? priority : priority_il, TS ? 16 : 2 * (int)sizeof(typename RT<R>::scalar), plan_radices<PL>(), &c2c, nullptr, nullptr};
+    }
+};
+
 // persistent TMA-pipelined r2c / c2r (scalar lanes)
 // XI: rows per tile of the c2r direction (1 = single-row tiles with shifted bulk copies, see k_real_pipe)
 template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false, int XI = X, bool HT = false> struct RealPipeLaunchers {

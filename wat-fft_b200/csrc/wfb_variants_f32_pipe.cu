@@ -7,6 +7,7 @@ namespace wfb {
 #define VP32(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, false, 32>::make(#PL "_pipe" #X, PRIO)
 #define VTS(PL, X, MINB, RC, PQ, PRIO) PipeLaunchers<float, PL, X, MINB, RC, PQ, true>::make(#PL "_pipe" #X "_ts", PRIO)
 #define VTSM(PL, X, MINB, RC, PQ, PRIO) PipeLaunchers<float, PL, X, MINB, RC, PQ, true>::make(#PL "_pipe" #X "_ts_m" #MINB, PRIO)
+#define VRP(PL, MINB, TS, NAME, PRIO) RegPipeLaunchers<float, PL, MINB, TS>::make(#PL NAME, PRIO)
 #define VP2(PL, X, MINB, PRIO) PipeLaunchers<f32x2, PL, X, MINB>::make(#PL "_pipe" #X "_x2", PRIO)
 const std::vector<Variant> &variants_f32_pipe() {
     // 16 KB tiles are the sweet spot for the dynamically scheduled pipeline (8 KB and 32 KB tiles lose 10-30 %).
@@ -29,6 +30,8 @@ const std::vector<Variant> &variants_f32_pipe() {
         VTS(P32_8192, 1, 1, false, 16, 61),
         // three resident CTAs per SM (85-register cap) for the barrier-heavy three-pass plans
         VTSM(F32_4096, 1, 3, false, 16, 19), VTSM(F32_2048, 1, 6, false, 16, 19),
+        // register-prefetch persistent kernels (k_c2c_rpf): the input never touches shared memory
+        VRP(F32_4096, 2, true, "_rpf_ts", 18), VRP(F32_4096, 2, false, "_rpf", 18), VRP(F32_2048, 3, true, "_rpf_ts", 18), VRP(F32_2048, 4, false, "_rpf", 18),
         VP64(P64_4096, 1, 1, 31),   // one exchange: 3 % slower than F32_4096_pipe1 at burst clocks, 4 % faster power-capped
          VP64(P64_2048, 1, 1, 20), VP64(P64_1024, 2, 1, 20),
     };
