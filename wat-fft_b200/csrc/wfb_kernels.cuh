@@ -1360,9 +1360,20 @@ __global__ void __launch_bounds__(PL::T, MINB) k_c2c_rpf(const __grid_constant__
 //     drain their own store group (cp.async.bulk.wait_group.read) right before the refill -- after the row
 //     loads of the current tile, which gives the store engine that time for free.
 // ----------------------------------------------------------------------------------------
+// Bytes per bulk copy.  Every copy is issued by one lane through a uniform-datapath instruction (UBLKCP), which the
+// compiler wraps in an elect / R2UR / branch sequence of ~9 instructions per lane and copy: at 512 bytes the N = 64
+// split kernel spends 64 copies x 9 = 30 % of its instructions (ncu r01: R2UR 15 %, PLOP3 13 %) issuing them, all
+// serialised in the one warp that also does the arithmetic.  1024-byte groups halve that where the row is wide enough
+// for the arithmetic to matter (N = 64 split: +2.3 % under the power cap; N = 16, 32 and the interleaved rows: no
+// change or -0.7 %, they keep 512).  -DWFB_TPIPE_GROUP_BYTES=n forces one size everywhere (A/B builds).
 template <typename R, class PL, int IO> __host__ __device__ constexpr int tpipe_group() {
     const int row_bytes = (IO == IO_SPLIT ? 1 : 2) * (int)sizeof(R) * PL::N;   // bytes of one row in one plane
-    return row_bytes >= 512 ? 1 : 512 / row_bytes;
+#ifdef WFB_TPIPE_GROUP_BYTES
+    const int group_bytes = WFB_TPIPE_GROUP_BYTES;
+#else
+    const int group_bytes = (IO == IO_SPLIT && sizeof(R) == 4 && PL::N >= 64) ? 1024 : 512;
+#endif
+    return row_bytes >= group_bytes ? 1 : group_bytes / row_bytes;
 }
 template <typename R, class PL, int X, int IO> __host__ __device__ constexpr size_t tpipe_buf_bytes() {
     constexpr int G = tpipe_group<R, PL, IO>();
