@@ -110,6 +110,8 @@ export interface FFT {
   readonly exports: FFTExports;
 
   /** NEW: frees device and pinned host memory; idempotent; any later use throws */
+  /** Staging knob of the H2D -> kernel -> D2H pipeline (see OPTIONS); contexts created with batch > 1 only. */
+  setOption(option: number, value: number): void;
   dispose(): void;
 }
 
@@ -123,6 +125,8 @@ export interface FFTf32 {
   forward(): void;
   inverse(): void;
   readonly exports: FFTf32Exports;
+  /** Staging knob of the H2D -> kernel -> D2H pipeline (see OPTIONS); contexts created with batch > 1 only. */
+  setOption(option: number, value: number): void;
   dispose(): void;
 }
 
@@ -151,6 +155,8 @@ export interface RFFT {
   inverse(): void;
 
   readonly exports: RFFTExports;
+  /** Staging knob of the H2D -> kernel -> D2H pipeline (see OPTIONS); contexts created with batch > 1 only. */
+  setOption(option: number, value: number): void;
   dispose(): void;
 }
 
@@ -165,6 +171,8 @@ export interface RFFTf32 {
   forward(): void;
   inverse(): void;
   readonly exports: RFFTf32Exports;
+  /** Staging knob of the H2D -> kernel -> D2H pipeline (see OPTIONS); contexts created with batch > 1 only. */
+  setOption(option: number, value: number): void;
   dispose(): void;
 }
 
@@ -181,6 +189,8 @@ export interface FFTf32Split {
   forward(): void;
   inverse(): void;
   readonly exports: FFTf32SplitExports;
+  /** Staging knob of the H2D -> kernel -> D2H pipeline (see OPTIONS); contexts created with batch > 1 only. */
+  setOption(option: number, value: number): void;
   dispose(): void;
 }
 
@@ -243,3 +253,6 @@ export function createSplitExports(options?: GpuOptions): Promise<FFTf32SplitExp
 
 /** NEW: number of CUDA devices visible to the process */
 export function deviceCount(): number;
+
+/** Option ids for `ctx.setOption()` (WFB_OPT_* of include/watfft_b200.h). */
+export const OPTIONS: Readonly<{ MAPPED_MAX_BYTES: 0; STAGE_CHUNK_BYTES: 1; STAGE_STREAMS: 2; STAGE_RAMP: 3 }>;

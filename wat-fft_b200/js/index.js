@@ -174,6 +174,12 @@ function makeContext({ moduleName, kind, layout, precision, size, options, preco
       if (exportsObj === null) exportsObj = makeInstanceSync(moduleName, { device });
       return exportsObj;
     },
+    /** staging knobs of wfb_exec (OPTIONS below = WFB_OPT_* of include/watfft_b200.h); contexts with batch > 1 */
+    setOption(option, value) {
+      alive();
+      if (plan === null) throw new Error("watfft_b200: setOption applies to contexts created with batch > 1");
+      n.planSetOption(plan, option, value);
+    },
     forward() { alive(); if (batch === 1) exportsObj[fwd](size); else n.exec(plan, FORWARD); },
     inverse() { alive(); if (batch === 1) exportsObj[inv](size); else n.exec(plan, INVERSE); },
     dispose() { // idempotent; later use throws instead of touching freed memory
@@ -249,3 +255,6 @@ export async function createFFTf32Split(size, options) {
 }
 
 export function deviceCount() { return native().deviceCount(); }
+
+/** Option ids for ctx.setOption(): zero-copy threshold, chunk size / streams / ramp of the H2D -> kernel -> D2H pipeline. */
+export const OPTIONS = Object.freeze({ MAPPED_MAX_BYTES: 0, STAGE_CHUNK_BYTES: 1, STAGE_STREAMS: 2, STAGE_RAMP: 3 });
