@@ -75,12 +75,13 @@ def test_c2c_f32_many_tiles(wf, oracle, n, layout):
 
 
 @pytest.mark.parametrize("layout", ["split", "interleaved"])
-@pytest.mark.parametrize("n", [2048, 4096])
-def test_c2c_f32_register_prefetch_many_tiles(wf, oracle, n, layout):
-    """The register-prefetch persistent kernels (k_c2c_rpf: the next transform is loaded into a second register set while
-    the current one is computed; results leave through two alternating shared-memory tiles): many tiles per CTA, an odd
-    tile count, both directions.  Same plan and twiddles as the default kernel, so the whole batch must match it BITWISE;
-    sampled rows against the oracle; repeated launches identical."""
+@pytest.mark.parametrize("n,tag", [(2048, "_rpf"), (4096, "_rpf"), (128, "_ts_g")])
+def test_c2c_f32_alternate_persistent_kernels_many_tiles(wf, oracle, n, tag, layout):
+    """Persistent alternates of the default kernel on the same plan: the register-prefetch kernels (k_c2c_rpf: the next
+    transform is loaded into a second register set while the current one is computed; results leave through two alternating
+    shared-memory tiles) and the grouped row copies of k_c2c_pipe (several rows per bulk copy, thread groups of a warp in
+    different copy groups).  Many tiles per CTA, a ragged last tile, both directions.  Same plan and twiddles as the default
+    kernel, so the whole batch must match it BITWISE; sampled rows against the oracle; repeated launches identical."""
     torch, dev = _torch()
     C = wf._cabi
     batch = TARGET_BYTES // (8 * n) + 3
@@ -92,11 +93,12 @@ def test_c2c_f32_register_prefetch_many_tiles(wf, oracle, n, layout):
     ptr = lambda t: t.data_ptr() if t is not None else None
     plan = wf.Plan(C.C2C, C.F32, C.SPLIT if split else C.INTERLEAVED, n, batch, 0, flags)
     names = plan.variants()
-    rpf = [i for i, v in enumerate(names) if "_rpf" in v]
-    assert rpf, names
+    rpf = [i for i, v in enumerate(names) if tag in v]
+    base = next(i for i, v in enumerate(names) if tag not in v)      # the established kernel on the same plan
+    assert rpf and ("_ts" in names[base]), names
     for direction in (C.FORWARD, C.INVERSE):
         ref0, ref1 = torch.empty_like(a0), (torch.empty_like(a1) if split else None)
-        plan.set_variant(0)
+        plan.set_variant(base)
         plan.exec_device(direction, (ptr(a0), ptr(a1)), (ptr(ref0), ptr(ref1)))
         plan.sync()
         for vi in rpf:

@@ -1016,7 +1016,7 @@ template <typename R, class PL, int PADQ, int X> __host__ __device__ constexpr s
 // stores issued after the next loop-top barrier, instead of per-thread STG; the stage is refilled once those
 // stores have drained (cp.async.bulk.wait_group.read), which the issuing lanes check after the row loads of the
 // following tile.
-template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, bool RC = false, bool TS = false, bool HT = false>
+template <typename R, class PL, int X, int PADQ, int IO, bool INV, int MINB, int RC = 0, bool TS = false, bool HT = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid(), "plan does not factor N");
     static_assert(!TS || RT<R>::LANES == 1, "TMA stores: scalar lanes");
@@ -1027,15 +1027,27 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
     constexpr int N = PL::N;
     constexpr int LAST = PL::npass() - 1;
     constexpr int ROWS = X * LANES;                 // rows per CTA iteration
-    // RC ("row copies"): one bulk copy per row into rows padded by N/16 elements, so that the
-    // 32/T rows a warp reads side by side start T banks apart (a dense tile puts every row on
-    // bank 0: ncu showed 4-way conflicts and mio_throttle as the top stall at N = 128)
-    constexpr int RSTR = RC ? N + N / 16 : N;       // smem row stride, elements
-    static_assert(!RC || RSTR <= padded_size<PADQ>(N), "padded rows must fit the stage buffer (sized for the scratch)");
-    static_assert(!RC || (N >= 64 && PL::T * X >= 32), "row copies need 16-byte aligned padded rows and a full issuing warp");
+    // RC > 0 ("row copies"): the tile arrives as groups of RC consecutive rows, one bulk copy per group and plane, with
+    // N/16 elements of padding behind every group, and the 32/T thread groups of a warp work on rows of 32/T DIFFERENT
+    // groups: the rows a warp reads side by side then start T banks apart (a dense tile puts every row on bank 0: ncu
+    // showed 4-way conflicts and mio_throttle as the top stall at N = 128).  RC = 1 is one copy per row; larger groups
+    // mean fewer copies -- each one costs the issuing warp ~9 instructions of elect / R2UR / branch per lane, while the
+    // CTA's other warps wait at the barrier (ncu r02, N = 128 with RC = 1: barrier 39 % of the stall samples, a fifth
+    // of the instructions in those loops).
+    constexpr int RG = RC > 0 ? RC : 1;             // rows per copy group
+    constexpr int NGR = ROWS / RG;                  // groups per tile
+    constexpr int GSTR = RG * N + N / 16;           // smem group stride, elements (RC only)
+    constexpr int PSTR = RC ? NGR * GSTR : ROWS * N;   // plane stride (split layout), elements
+    static_assert(!RC || (ROWS % RG == 0 && NGR >= 32 / PL::T && LANES == 1), "a warp's thread groups must land in distinct copy groups");
+    static_assert(!RC || (size_t)(IO == IO_SPLIT ? 2 : 1) * NGR * GSTR * (IO == IO_SPLIT ? 1 : 2) * sizeof(typename VecOf<R>::s) <= pipe_buf_bytes<R, PL, PADQ, X>(),
+                  "the padded groups must fit the stage buffer (sized for the scratch)");
+    static_assert(!RC || (N >= 64 && PL::T * X >= 32), "row copies need 16-byte aligned padded groups and a full issuing warp");
     constexpr size_t BUF = pipe_buf_bytes<R, PL, PADQ, X>();
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * BUF);
     const int xi = threadIdx.x / PL::T, tid = threadIdx.x % PL::T;
+    // row of the tile this thread group works on, and where that row sits in the stage buffer (elements)
+    const int xr = RC ? (xi % NGR) * RG + xi / NGR : xi;
+    const int roff = RC ? (xr / RG) * GSTR + (xr % RG) * N : xi * LANES * N;
     const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
     const long tiles = (p.batch + ROWS - 1) / ROWS;
 
@@ -1047,30 +1059,32 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
     __syncthreads();
 
     // stream a tile's rows into stage st: thread 0 (dense tile: one copy per plane) or warp 0
-    // (row copies: one copy per row and plane, spread over the lanes)
+    // (row copies: one copy per group and plane, spread over the lanes)
     auto issue = [&](long tile, int st) {
         const long row = tile * ROWS;
         const int rows = (p.batch - row < ROWS) ? (int)(p.batch - row) : ROWS;
         unsigned char *dst = smem_raw + st * BUF;
         constexpr int PLANES = (IO == IO_SPLIT) ? 2 : 1;
         constexpr uint32_t ROWB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * N * sizeof(S));     // bytes per row per plane
-        constexpr uint32_t RSB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * RSTR * sizeof(S));  // smem row stride, bytes
+        constexpr uint32_t ESB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * sizeof(S));         // bytes per element per plane
         if constexpr (TS) { bulk_wait_read_all(); __syncwarp(); }   // the stores out of this stage have drained
         if constexpr (!RC) {
             if (threadIdx.x == 0) {
                 mbar_expect_tx(mbar + st, PLANES * rows * ROWB);
                 tma_load_1d(dst, reinterpret_cast<const unsigned char *>(p.in0) + row * ROWB, rows * ROWB, mbar + st);
                 if constexpr (PLANES == 2)
-                    tma_load_1d(dst + ROWS * RSB, reinterpret_cast<const unsigned char *>(p.in1) + row * ROWB, rows * ROWB, mbar + st);
+                    tma_load_1d(dst + PSTR * ESB, reinterpret_cast<const unsigned char *>(p.in1) + row * ROWB, rows * ROWB, mbar + st);
             }
         } else {
             if (threadIdx.x < 32) {
                 if (threadIdx.x == 0) mbar_expect_tx(mbar + st, PLANES * rows * ROWB);
                 __syncwarp();
-                for (int c = threadIdx.x; c < PLANES * rows; c += 32) {
-                    const int pl = c / rows, r = c - pl * rows;
-                    const unsigned char *src = reinterpret_cast<const unsigned char *>(pl ? p.in1 : p.in0) + (row + r) * ROWB;
-                    tma_load_1d(dst + (size_t)(pl * ROWS + r) * RSB, src, ROWB, mbar + st);
+                const int groups = (rows + RG - 1) / RG;
+                for (int c = threadIdx.x; c < PLANES * groups; c += 32) {
+                    const int pl = c / groups, g = c - pl * groups;
+                    const int nr = rows - g * RG < RG ? rows - g * RG : RG;
+                    const unsigned char *src = reinterpret_cast<const unsigned char *>(pl ? p.in1 : p.in0) + (row + (long)g * RG) * ROWB;
+                    tma_load_1d(dst + (size_t)(pl * PSTR + g * GSTR) * ESB, src, nr * ROWB, mbar + st);
                 }
             }
         }
@@ -1083,19 +1097,21 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         const unsigned char *src = smem_raw + st * BUF;
         constexpr int PLANES = (IO == IO_SPLIT) ? 2 : 1;
         constexpr uint32_t ROWB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * N * sizeof(S));
-        constexpr uint32_t RSB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * RSTR * sizeof(S));
+        constexpr uint32_t ESB = (uint32_t)((IO == IO_SPLIT ? 1 : 2) * sizeof(S));
         if (threadIdx.x < 32) {
             if constexpr (!RC) {
                 if (threadIdx.x == 0) {
                     tma_store_1d(reinterpret_cast<unsigned char *>(p.out0) + row * ROWB, src, rows * ROWB);
                     if constexpr (PLANES == 2)
-                        tma_store_1d(reinterpret_cast<unsigned char *>(p.out1) + row * ROWB, src + ROWS * RSB, rows * ROWB);
+                        tma_store_1d(reinterpret_cast<unsigned char *>(p.out1) + row * ROWB, src + PSTR * ESB, rows * ROWB);
                 }
             } else {
-                for (int c = threadIdx.x; c < PLANES * rows; c += 32) {
-                    const int pl = c / rows, r = c - pl * rows;
-                    unsigned char *dst = reinterpret_cast<unsigned char *>(pl ? p.out1 : p.out0) + (row + r) * ROWB;
-                    tma_store_1d(dst, src + (size_t)(pl * ROWS + r) * RSB, ROWB);
+                const int groups = (rows + RG - 1) / RG;
+                for (int c = threadIdx.x; c < PLANES * groups; c += 32) {
+                    const int pl = c / groups, g = c - pl * groups;
+                    const int nr = rows - g * RG < RG ? rows - g * RG : RG;
+                    unsigned char *dst = reinterpret_cast<unsigned char *>(pl ? p.out1 : p.out0) + (row + (long)g * RG) * ROWB;
+                    tma_store_1d(dst, src + (size_t)(pl * PSTR + g * GSTR) * ESB, nr * ROWB);
                 }
             }
             bulk_commit();
@@ -1123,13 +1139,14 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
         if constexpr (!TS) claim_and_issue<(PL::N <= 256)>(p.ctr, pending, tiles, slot, st ^ 1, issue);
         mbar_wait(mbar + st, (it >> 1) & 1);
 
-        const long row = tile * ROWS + (long)xi * LANES;
+        const long row = tile * ROWS + (long)xr * LANES;
         const bool active = row < p.batch;
         const bool two = LANES == 2 && row + 1 < p.batch;
         unsigned char *buf = smem_raw + st * BUF;
         if constexpr (IO == IO_SPLIT) {
-            const S *re = reinterpret_cast<const S *>(buf) + (size_t)xi * LANES * RSTR + tid;
-            const S *im = re + ROWS * RSTR;
+            constexpr int RSTR = N;                 // next row of a lane pair (packed lanes: dense tiles only)
+            const S *re = reinterpret_cast<const S *>(buf) + roff + tid;
+            const S *im = re + PSTR;
             static_for<PL::E>([&](auto E_) {
                 CIDX(e, E_);
                 if constexpr (LANES == 2) {
@@ -1140,7 +1157,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
                 }
             });
         } else {
-            const V2 *z = reinterpret_cast<const V2 *>(buf) + (size_t)xi * LANES * RSTR + tid;
+            constexpr int RSTR = N;
+            const V2 *z = reinterpret_cast<const V2 *>(buf) + roff + tid;
             static_for<PL::E>([&](auto E_) {
                 CIDX(e, E_);
                 if constexpr (LANES == 2) {
@@ -1166,8 +1184,8 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
             if constexpr (PL::npass() > 1) __syncthreads();
             const R sc = RT<R>::splat((S)p.scale);
             if constexpr (IO == IO_SPLIT) {
-                S *re = reinterpret_cast<S *>(buf) + (size_t)xi * RSTR + tid;
-                S *im = re + ROWS * RSTR;
+                S *re = reinterpret_cast<S *>(buf) + roff + tid;
+                S *im = re + PSTR;
                 static_for<PL::E>([&](auto S_) {
                     CIDX(slot_, S_);
                     constexpr int e = out_elem<PL, LAST>(slot_);
@@ -1176,7 +1194,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
                     re[e * PL::T] = v.x; im[e * PL::T] = v.y;
                 });
             } else {
-                V2 *z = reinterpret_cast<V2 *>(buf) + (size_t)xi * RSTR + tid;
+                V2 *z = reinterpret_cast<V2 *>(buf) + roff + tid;
                 static_for<PL::E>([&](auto S_) {
                     CIDX(slot_, S_);
                     constexpr int e = out_elem<PL, LAST>(slot_);

@@ -79,7 +79,7 @@ template <typename R, class PL, int X, int MINB, bool SPLIT_IO> struct Launchers
 };
 
 // persistent TMA-pipelined c2c: grid = resident CTAs, each loops over tiles of X*LANES rows
-template <typename R, class PL, int X, int MINB, bool RC = false, int PQ = PADQ, bool TS = false, bool HT = false> struct PipeLaunchers {
+template <typename R, class PL, int X, int MINB, int RC = 0, int PQ = PADQ, bool TS = false, bool HT = false> struct PipeLaunchers {
     static constexpr size_t smem = 2 * pipe_buf_bytes<R, PL, PQ, X>() + 64;
     static constexpr int LANES = RT<R>::LANES;
     static long tiles(long batch) { return (batch + X * LANES - 1) / (X * LANES); }

@@ -3,14 +3,14 @@
 namespace wfb {
 #define VP(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB>::make(#PL "_pipe" #X, PRIO)
 #define VR(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB>::make(#PL "_rpipe" #X, __VA_ARGS__)
-#define VTS(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_pipe" #X "_ts", PRIO)
-#define VRTS(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_rpipe" #X "_ts", __VA_ARGS__)
+#define VTS(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB, 0, PADQ, true>::make(#PL "_pipe" #X "_ts", PRIO)
+#define VRTS(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, 0, PADQ, true>::make(#PL "_rpipe" #X "_ts", __VA_ARGS__)
 // + the last pass's twiddles held in registers across tiles (HT, see hoist_load in wfb_kernels.cuh)
-#define VTSH(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB, false, PADQ, true, true>::make(#PL "_pipe" #X "_ts_ht", PRIO)
-#define VRTSH(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true, X, true>::make(#PL "_rpipe" #X "_ts_ht", __VA_ARGS__)
+#define VTSH(PL, X, MINB, PRIO) PipeLaunchers<double, PL, X, MINB, 0, PADQ, true, true>::make(#PL "_pipe" #X "_ts_ht", PRIO)
+#define VRTSH(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, 0, PADQ, true, X, true>::make(#PL "_rpipe" #X "_ts_ht", __VA_ARGS__)
 // + a higher minimum of resident CTAs (the register cap that goes with it): the f64 real kernels run 8 warps per SM
-#define VRTSM(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true>::make(#PL "_rpipe" #X "_ts_m" #MINB, __VA_ARGS__)
-#define VRTSHM(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, false, PADQ, true, X, true>::make(#PL "_rpipe" #X "_ts_ht_m" #MINB, __VA_ARGS__)
+#define VRTSM(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, 0, PADQ, true>::make(#PL "_rpipe" #X "_ts_m" #MINB, __VA_ARGS__)
+#define VRTSHM(PL, X, MINB, ...) RealPipeLaunchers<double, PL, X, MINB, 0, PADQ, true, X, true>::make(#PL "_rpipe" #X "_ts_ht_m" #MINB, __VA_ARGS__)
 const std::vector<Variant> &variants_f64_pipe() {
     // priorities from the sweeps in profiles/ (c2c N = 256: the direct kernel wins; real transforms: the pipelined
     // kernels win up to N = 2048 since the Hermitian step moves only half its data through shared memory)
