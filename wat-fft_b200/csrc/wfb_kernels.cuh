@@ -1380,21 +1380,27 @@ __global__ void __launch_bounds__(PL::T, MINB) k_c2c_rpf(const __grid_constant__
 // ----------------------------------------------------------------------------------------
 // Bytes per bulk copy.  Every copy is issued by one lane through a uniform-datapath instruction (UBLKCP), which the
 // compiler wraps in an elect / R2UR / branch sequence of ~9 instructions per lane and copy: at 512 bytes the N = 64
-// split kernel spends 64 copies x 9 = 30 % of its instructions (ncu r01: R2UR 15 %, PLOP3 13 %) issuing them, all
-// serialised in the one warp that also does the arithmetic.  1024-byte groups halve that where the row is wide enough
-// for the arithmetic to matter (N = 64 split: +2.3 % under the power cap; N = 16, 32 and the interleaved rows: no
-// change or -0.7 %, they keep 512).  -DWFB_TPIPE_GROUP_BYTES=n forces one size everywhere (A/B builds).
-template <typename R, class PL, int IO> __host__ __device__ constexpr int tpipe_group() {
+// split kernel spent 64 copies x 9 = 30 % of its instructions (ncu r01: R2UR 15 %, PLOP3 13 %) issuing them, all
+// serialised in the one warp that also does the arithmetic.  Wider groups mean fewer copies where the row is wide
+// enough for the arithmetic to matter: N = 64 split moves 1024 bytes per copy with 32-row tiles (+2.3 % under the
+// power cap) and 2048 bytes with 64-row tiles (two warps per CTA, the default: another +1 %); N = 16, 32 and the
+// interleaved rows keep 512 (no change or -0.7 % with more).  A tile always has at least 8 groups (the lane <-> row
+// mapping below needs them).  -DWFB_TPIPE_GROUP_BYTES=n forces one size everywhere (A/B builds).
+#ifndef WFB_TPIPE_WIDE_GROUP_BYTES
+#define WFB_TPIPE_WIDE_GROUP_BYTES 2048
+#endif
+template <typename R, class PL, int IO, int X> __host__ __device__ constexpr int tpipe_group() {
     const int row_bytes = (IO == IO_SPLIT ? 1 : 2) * (int)sizeof(R) * PL::N;   // bytes of one row in one plane
 #ifdef WFB_TPIPE_GROUP_BYTES
     const int group_bytes = WFB_TPIPE_GROUP_BYTES;
 #else
-    const int group_bytes = (IO == IO_SPLIT && sizeof(R) == 4 && PL::N >= 64) ? 1024 : 512;
+    const int group_bytes = (IO == IO_SPLIT && sizeof(R) == 4 && PL::N >= 64) ? WFB_TPIPE_WIDE_GROUP_BYTES : 512;
 #endif
-    return row_bytes >= group_bytes ? 1 : group_bytes / row_bytes;
+    const int g = row_bytes >= group_bytes ? 1 : group_bytes / row_bytes;
+    return g > X / 8 ? X / 8 : g;                      // at least 8 groups per tile (lane <-> row mapping below)
 }
 template <typename R, class PL, int X, int IO> __host__ __device__ constexpr size_t tpipe_buf_bytes() {
-    constexpr int G = tpipe_group<R, PL, IO>();
+    constexpr int G = tpipe_group<R, PL, IO, X>();
     return ((size_t)(G * 2 * sizeof(R) * PL::N + 16) * (X / G) + 127) / 128 * 128;
 }
 
@@ -1405,7 +1411,7 @@ __global__ void __launch_bounds__(X, MINB) k_c2c_tpipe(const __grid_constant__ K
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int N = PL::N;
     constexpr int ES = (int)sizeof(R);                 // bytes of a real
-    constexpr int G = tpipe_group<R, PL, IO>();        // rows per bulk copy
+    constexpr int G = tpipe_group<R, PL, IO, X>();     // rows per bulk copy
     constexpr int NG = X / G;                          // groups per tile
     static_assert(X % G == 0 && NG % 8 == 0, "8 consecutive lanes must sit in 8 consecutive groups");
     constexpr int GSTR = G * 2 * ES * N + 16;          // group stride, bytes (odd multiple of 16)

@@ -13,7 +13,7 @@ const std::vector<Variant> &variants_f32_tile() {
     static const std::vector<Variant> v = {
         V(F32_4, 256, 2, 50), V(F32_8, 256, 2, 50), V(F32_16, 256, 2, 50), V(T32_32, 128, 2, 50), V(T32_64, 128, 1, 50),
         VX(T32_64, 32, 1, 52), VX(T32_32, 64, 2, 52), VX(F32_16, 128, 2, 51),
-        VTP(T32_64, 32, 1, 55), VTP(T32_32, 64, 2, 55), VTP(F32_16, 128, 2, 55),
+        VTP(T32_64, 32, 1, 55), VTP(T32_32, 64, 2, 55), VTP(F32_16, 128, 2, 55), VTP(T32_64, 64, 1, 56, -1, 54),
         VRTP(T32_64, 32, 1, 55), VRTP(T32_32, 64, 2, 55),
         VR(F32_16, 256, 2, 50), VR(T32_32, 128, 2, 50), VRX(F32_4, 128, 2, 51), VRX(F32_8, 128, 2, 51), VRX(T32_64, 32, 1, 26, 32), VRX(T32_32, 32, 2, 51), VRX(F32_16, 64, 2, 51),
     };
