@@ -157,6 +157,11 @@ WFB_API size_t wfb_plan_algorithmic_bytes(wfb_plan *plan);
 enum { WFB_OPT_MAPPED_MAX_BYTES = 0, WFB_OPT_STAGE_CHUNK_BYTES = 1, WFB_OPT_STAGE_STREAMS = 2, WFB_OPT_STAGE_RAMP = 3 };
 WFB_API int wfb_plan_set_option(wfb_plan *plan, int option, long value);
 WFB_API long wfb_plan_get_option(wfb_plan *plan, int option);
+/* The chunk schedule wfb_exec uses for a batch (pure host logic, no GPU needed): rows per chunk of the H2D / kernel / D2H
+ * pipeline for `batch` rows whose widest plane has `widest_row_bytes` per row, with WFB_OPT_STAGE_CHUNK_BYTES =
+ * chunk_bytes and WFB_OPT_STAGE_RAMP = ramp.  Writes up to `capacity` entries and returns the number of chunks (0 when the
+ * batch is small enough for one staged copy; a negative error code for bad arguments). */
+WFB_API int wfb_stage_schedule(long batch, size_t widest_row_bytes, long chunk_bytes, int ramp, long *rows_out, int capacity);
 /* Which path the latest wfb_exec took. */
 enum { WFB_PATH_NONE = 0, WFB_PATH_STAGED = 1, WFB_PATH_PIPELINED = 2, WFB_PATH_MAPPED = 3 };
 WFB_API int wfb_plan_last_path(wfb_plan *plan);

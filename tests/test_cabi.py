@@ -159,3 +159,50 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)       # pure host logic: runs without a GPU
     assert r.returncode == 0, (r.returncode, r.stderr)
 
+
+
+def test_stage_schedule_properties(wf):
+    """The chunk schedule of wfb_exec's H2D / kernel / D2H pipeline (pure host logic, exported for this test): for any
+    batch, row width, chunk size and ramp setting the chunks tile the batch exactly; every chunk start is 16-byte aligned for
+    the (n+2)-wide spectrum rows (all chunks but the last hold an even number of rows); steady-state chunks hold whole kernel
+    tiles; and with the ramp on, the first and the last three chunks are the 1/8, 1/4, 1/2 steps around full-size ones."""
+    import ctypes
+    lib = wf._cabi.lib()
+    rng = np.random.default_rng(11)
+    out = (ctypes.c_long * 4096)()
+    seen_ramped = seen_flat = seen_single = 0
+    for _ in range(4000):
+        row = int(rng.choice([8, 64, 264, 1024, 4104, 16392, 65536, 131088]))
+        chunk_bytes = int(rng.choice([4096, 32 << 10, 1 << 20, 32 << 20]))
+        batch = int(rng.integers(1, 200000)) if rng.random() < 0.8 else int(2 ** rng.integers(0, 24))
+        ramp = int(rng.integers(0, 2))
+        n = lib.wfb_stage_schedule(batch, row, chunk_bytes, ramp, out, 4096)
+        chunk = max(1, chunk_bytes // row)
+        chunk = chunk & ~255 if chunk >= 512 else (chunk & ~1 if chunk >= 2 else chunk)
+        if batch <= 2 * chunk:
+            assert n == 0
+            seen_single += 1
+            continue
+        if n > 4096:
+            continue                                          # (tiny chunks of a huge batch: only the count is returned)
+        rows = list(out[:n])
+        assert n >= 3 and sum(rows) == batch and min(rows) >= 1, (batch, row, chunk_bytes, ramp, rows[:8])
+        if chunk >= 2:
+            assert all(r % 2 == 0 for r in rows[:-1]), (batch, row, chunk_bytes, ramp)
+        assert max(rows) <= chunk + 1
+        ramped = ramp and chunk >= 16 and rows[0] < chunk
+        if ramped:
+            seen_ramped += 1
+            up = rows[:3]
+            assert up[0] <= up[1] <= up[2] <= chunk and up[2] >= chunk // 2 - 255
+            down = rows[-3:]
+            assert down[0] >= down[1] >= down[2] - 1
+            assert rows[3] == chunk                           # at least two full chunks in the middle
+            if chunk >= 512:
+                assert all(r % 256 == 0 for r in rows[3:-4] if r == chunk)
+        else:
+            seen_flat += 1
+            assert all(r == chunk for r in rows[:-1])
+    assert seen_ramped > 200 and seen_flat > 200 and seen_single > 50
+    assert lib.wfb_stage_schedule(0, 8, 4096, 1, out, 4096) < 0
+    assert lib.wfb_stage_schedule(10, 0, 4096, 1, out, 4096) < 0

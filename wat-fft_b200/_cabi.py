@@ -60,6 +60,7 @@ SYMBOLS = {
     "wfb_plan_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_long]),
     "wfb_plan_get_option": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_int]),
     "wfb_plan_last_path": (ctypes.c_int, [ctypes.c_void_p]),
+    "wfb_stage_schedule": (ctypes.c_int, [ctypes.c_long, ctypes.c_size_t, ctypes.c_long, ctypes.c_int, ctypes.POINTER(ctypes.c_long), ctypes.c_int]),
     "wfb_pcie_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "wfb_pcie_probe_open": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "wfb_pcie_probe_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),

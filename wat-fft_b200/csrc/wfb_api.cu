@@ -769,6 +769,36 @@ static bool arena_lookup(const void *p, size_t need, void **dev_alias) {
     return true;
 }
 
+// Rows per pipeline chunk of wfb_exec: `chunk_bytes` of the widest plane, whole kernel tiles (tiles hold up to 256 rows)
+// and 16-byte aligned chunk starts for the (n+2)-wide spectrum rows (an even number of rows).
+static long stage_chunk_rows(long chunk_bytes, size_t widest_row_bytes) {
+    long chunk = (long)(chunk_bytes / (long)widest_row_bytes);
+    if (chunk >= 512) chunk &= ~255L; else if (chunk >= 2) chunk &= ~1L;
+    return chunk < 1 ? 1 : chunk;
+}
+// Chunk schedule of the pipelined path (batch > 2 * chunk).  The first H2D copy has no D2H running beside it and the last
+// D2H no H2D: those two ends are the part of the call that cannot overlap, so with `ramp` the schedule goes up through
+// short chunks (1/8, 1/4, 1/2 of the steady-state size) and down again.  Every chunk but the last keeps the alignment
+// rules of stage_chunk_rows; the rows of the chunks add up to `batch`.
+static std::vector<long> stage_schedule(long batch, long chunk, bool ramp_on) {
+    std::vector<long> sched;
+    auto aligned = [](long c) { if (c >= 512) c &= ~255L; else if (c >= 2) c &= ~1L; return c < 1 ? 1L : c; };
+    const long ramp[3] = {aligned(chunk / 8), aligned(chunk / 4), aligned(chunk / 2)};
+    const long ends = 2 * (ramp[0] + ramp[1] + ramp[2]);
+    if (ramp_on && chunk >= 16 && batch >= ends + 2 * chunk) {
+        long mid = batch - ends;
+        for (int i = 0; i < 3; i++) sched.push_back(ramp[i]);
+        for (; mid >= chunk; mid -= chunk) sched.push_back(chunk);
+        const long rem = mid >= 2 ? (mid & ~1L) : 0;      // an even remainder keeps the next chunk start aligned
+        if (rem) sched.push_back(rem);
+        for (int i = 2; i >= 0; i--) sched.push_back(ramp[i]);
+        sched.back() += mid - rem;                         // (an odd batch's last row)
+    } else {
+        for (long r0 = 0; r0 < batch; r0 += chunk) sched.push_back(batch - r0 < chunk ? batch - r0 : chunk);
+    }
+    return sched;
+}
+
 // wfb_exec / wfb_exec_host: `hs`, `hd` = host addresses of the planes read and written (indexed like src[] / dst[] below),
 // `as`, `ad` = the device-side addresses of the same bytes (zero-copy path; null when the memory is not mapped)
 static int exec_impl(wfb_plan *pl, int direction, int flags, void *const hs_in[2], void *const hd_in[2], void *const as_in[2], void *const ad_in[2]) {
@@ -831,10 +861,7 @@ static int exec_impl(wfb_plan *pl, int direction, int flags, void *const hs_in[2
     // full PCIe rate while there are enough chunks to overlap the two directions
     size_t widest = src_row[0] > dst_row[0] ? src_row[0] : dst_row[0];
     const int nstreams = pl->stage_streams;
-    long chunk = (long)(pl->stage_chunk_bytes / (long)widest);
-    // whole tiles per chunk (tiles hold up to 256 rows) and 16-byte aligned chunk starts for the (n+2)-wide spectrum rows
-    if (chunk >= 512) chunk &= ~255L; else if (chunk >= 2) chunk &= ~1L;
-    if (chunk < 1) chunk = 1;
+    const long chunk = stage_chunk_rows(pl->stage_chunk_bytes, widest);
     const bool pipelined = (h2d || d2h) && pl->batch > 2 * chunk;
     if (!pipelined) {
         pl->last_path = WFB_PATH_STAGED;
@@ -855,26 +882,7 @@ static int exec_impl(wfb_plan *pl, int direction, int flags, void *const hs_in[2
         // order the pipeline after whatever is already queued on the plan's stream
         CK(cudaEventRecord(pl->start_ev, pl->stream));
         for (int i = 0; i < nstreams; i++) CK(cudaStreamWaitEvent(pl->pipe[i], pl->start_ev, 0));
-        // Chunk schedule.  The first H2D copy has no D2H running beside it and the last D2H no H2D: those two ends are
-        // the part of the call that cannot overlap, so the schedule ramps up through short chunks (1/8, 1/4, 1/2 of the
-        // steady-state size) and down again.  Every chunk but the last keeps the alignment rules above.
-        std::vector<long> sched;
-        {
-            auto aligned = [](long c) { if (c >= 512) c &= ~255L; else if (c >= 2) c &= ~1L; return c < 1 ? 1L : c; };
-            const long ramp[3] = {aligned(chunk / 8), aligned(chunk / 4), aligned(chunk / 2)};
-            const long ends = 2 * (ramp[0] + ramp[1] + ramp[2]);
-            if (pl->stage_ramp && chunk >= 16 && pl->batch >= ends + 2 * chunk) {
-                long mid = pl->batch - ends;
-                for (int i = 0; i < 3; i++) sched.push_back(ramp[i]);
-                for (; mid >= chunk; mid -= chunk) sched.push_back(chunk);
-                const long rem = mid >= 2 ? (mid & ~1L) : 0;      // an even remainder keeps the next chunk start aligned
-                if (rem) sched.push_back(rem);
-                for (int i = 2; i >= 0; i--) sched.push_back(ramp[i]);
-                sched.back() += mid - rem;                         // (an odd batch's last row)
-            } else {
-                for (long r0 = 0; r0 < pl->batch; r0 += chunk) sched.push_back(pl->batch - r0 < chunk ? pl->batch - r0 : chunk);
-            }
-        }
+        const std::vector<long> sched = stage_schedule(pl->batch, chunk, pl->stage_ramp);
         long r0 = 0;
         for (size_t c = 0; c < sched.size(); r0 += sched[c], c++) {
             const long rows = sched[c];
@@ -903,6 +911,15 @@ static int exec_impl(wfb_plan *pl, int direction, int flags, void *const hs_in[2
 }
 
 extern "C" {
+
+int wfb_stage_schedule(long batch, size_t widest_row_bytes, long chunk_bytes, int ramp, long *rows_out, int capacity) {
+    if (batch < 1 || widest_row_bytes < 1 || chunk_bytes < 1 || capacity < 0 || (capacity > 0 && !rows_out)) return WFB_ERR_BAD_ARG;
+    const long chunk = stage_chunk_rows(chunk_bytes, widest_row_bytes);
+    if (batch <= 2 * chunk) return 0;                      // not pipelined: one copy in, one launch, one copy out
+    const std::vector<long> sched = stage_schedule(batch, chunk, ramp != 0);
+    for (size_t i = 0; i < sched.size() && (int)i < capacity; i++) rows_out[i] = sched[i];
+    return (int)sched.size();
+}
 
 int wfb_exec(wfb_plan *pl, int direction, int flags) {
     if (!pl || (direction != WFB_FORWARD && direction != WFB_INVERSE)) return WFB_ERR_BAD_ARG;
