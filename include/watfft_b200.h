@@ -112,7 +112,9 @@ WFB_API void *wfb_device_buffer(wfb_plan *plan, int which);
 WFB_API int wfb_exec(wfb_plan *plan, int direction, int flags);
 
 /* Device-pointer entry (bench harness, multi-GPU driver).  d_in/d_out hold two plane pointers
- * (second unused unless C2C SPLIT).  `stream` is a cudaStream_t (NULL = the plan's stream).
+ * (second unused unless C2C SPLIT).  `stream` is a cudaStream_t (NULL = the plan's stream).  The plan's stream is
+ * NON-BLOCKING: it does not order against the legacy default stream, so a caller that produced the inputs on another
+ * stream passes that stream here, or synchronises first.
  * In-place (d_in == d_out) is allowed for C2C and for R2C at batch = 1. */
 WFB_API int wfb_exec_device(wfb_plan *plan, int direction, const void *const d_in[2], void *const d_out[2],
                             void *stream);

@@ -81,6 +81,7 @@ def test_full_size_properties_c2c(wf, oracle, n):
     im = torch.rand(batch * n, device=dev, generator=g) * 2 - 1
     ore, oim = torch.empty_like(re), torch.empty_like(im)
     plan = wf.Plan(C.C2C, C.F32, C.SPLIT, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     plan.exec_device(C.FORWARD, (re.data_ptr(), im.data_ptr()), (ore.data_ptr(), oim.data_ptr()))
     plan.sync()
     for r in sorted({0, 1, batch // 2, batch - 1}):
@@ -111,6 +112,7 @@ def test_full_size_properties_r2c(wf, oracle, n):
     spec = torch.empty(batch * (n + 2), device=dev)
     back = torch.empty_like(x)
     plan = wf.Plan(C.R2C, C.F32, 0, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
     plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))
     plan.sync()
@@ -136,6 +138,7 @@ def test_full_size_properties_f64(wf, oracle, n):
     z = torch.rand(batch * 2 * n, device=dev, generator=g, dtype=torch.float64) * 2 - 1
     out = torch.empty_like(z)
     plan = wf.Plan(C.C2C, C.F64, C.INTERLEAVED, n, batch, 0, flags)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     plan.exec_device(C.FORWARD, (z.data_ptr(), None), (out.data_ptr(), None))
     plan.sync()
     for r in sorted({0, 1, batch // 2, batch - 1}):
@@ -150,6 +153,7 @@ def test_full_size_properties_f64(wf, oracle, n):
     spec = out[: batch * (n + 2)]
     back = torch.empty_like(x)
     plan = wf.Plan(C.R2C, C.F64, 0, n, batch, 0, flags)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
     plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))
     plan.sync()
@@ -374,6 +378,7 @@ def test_exec_device_misaligned_pointers_fall_back(wf, oracle):
     d_re[pad:pad + batch * n] = torch.from_numpy(re.ravel()).to(dev)
     d_im[pad:pad + batch * n] = torch.from_numpy(im.ravel()).to(dev)
     plan = wf.Plan(C.C2C, C.F32, C.SPLIT, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     assert "pipe" in plan.variants()[0]                  # the default would be a TMA kernel
     plan.exec_device(C.FORWARD, (d_re.data_ptr() + 4 * pad, d_im.data_ptr() + 4 * pad),
                      (o_re.data_ptr() + 4 * pad, o_im.data_ptr() + 4 * pad))

@@ -41,6 +41,7 @@ def test_c2c_f32_many_tiles(wf, oracle, n, layout):
         im = torch.rand(batch * n, device=dev, generator=g) * 2 - 1
         ore, oim = torch.empty_like(re), torch.empty_like(im)
         plan = wf.Plan(C.C2C, C.F32, C.SPLIT, n, batch, 0, flags)
+        torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
         plan.exec_device(C.FORWARD, (re.data_ptr(), im.data_ptr()), (ore.data_ptr(), oim.data_ptr()))
         plan.sync()
         o2r, o2i = torch.empty_like(re), torch.empty_like(im)
@@ -62,6 +63,7 @@ def test_c2c_f32_many_tiles(wf, oracle, n, layout):
         z = torch.rand(batch * 2 * n, device=dev, generator=g) * 2 - 1
         o = torch.empty_like(z)
         plan = wf.Plan(C.C2C, C.F32, C.INTERLEAVED, n, batch, 0, flags)
+        torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
         plan.exec_device(C.FORWARD, (z.data_ptr(), None), (o.data_ptr(), None))
         plan.sync()
         for r in _rows(batch, n):
@@ -92,6 +94,7 @@ def test_c2c_f32_alternate_persistent_kernels_many_tiles(wf, oracle, n, tag, lay
     a1 = torch.rand(batch * n, device=dev, generator=g) * 2 - 1 if split else None
     ptr = lambda t: t.data_ptr() if t is not None else None
     plan = wf.Plan(C.C2C, C.F32, C.SPLIT if split else C.INTERLEAVED, n, batch, 0, flags)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     names = plan.variants()
     rpf = [i for i, v in enumerate(names) if tag in v]
     base = next(i for i, v in enumerate(names) if tag not in v)      # the established kernel on the same plan
@@ -106,6 +109,7 @@ def test_c2c_f32_alternate_persistent_kernels_many_tiles(wf, oracle, n, tag, lay
             o0, o1 = torch.empty_like(a0), (torch.empty_like(a1) if split else None)
             for rep in range(3):
                 o0.zero_()
+                torch.cuda.synchronize()
                 plan.exec_device(direction, (ptr(a0), ptr(a1)), (ptr(o0), ptr(o1)))
                 plan.sync()
                 assert torch.equal(o0, ref0) and (not split or torch.equal(o1, ref1)), (names[vi], direction, rep)
@@ -122,6 +126,7 @@ def test_c2c_f32_alternate_persistent_kernels_many_tiles(wf, oracle, n, tag, lay
     # in place (the contexts' call shape): the loads of the NEXT row are in flight while this row's results are stored
     plan.set_variant(rpf[0])
     b0, b1 = a0.clone(), (a1.clone() if split else None)
+    torch.cuda.synchronize()
     plan.exec_device(C.FORWARD, (ptr(b0), ptr(b1)), (ptr(b0), ptr(b1)))
     plan.exec_device(C.INVERSE, (ptr(b0), ptr(b1)), (ptr(b0), ptr(b1)))
     plan.sync()
@@ -139,6 +144,7 @@ def test_real_f32_many_tiles(wf, oracle, n):
     spec = torch.empty(batch * (n + 2), device=dev)
     back = torch.empty_like(x)
     plan = wf.Plan(C.R2C, C.F32, 0, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
     plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))
     plan.sync()
@@ -168,6 +174,7 @@ def test_c2c_f64_many_tiles(wf, oracle, n):
     z = torch.rand(batch * 2 * n, device=dev, generator=g, dtype=torch.float64) * 2 - 1
     o = torch.empty_like(z)
     plan = wf.Plan(C.C2C, C.F64, C.INTERLEAVED, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     plan.exec_device(C.FORWARD, (z.data_ptr(), None), (o.data_ptr(), None))
     plan.sync()
     o2 = torch.empty_like(o)
@@ -196,6 +203,7 @@ def test_real_f64_many_tiles(wf, oracle, n):
     spec = torch.empty(batch * (n + 2), device=dev, dtype=torch.float64)
     back = torch.empty_like(x)
     plan = wf.Plan(C.R2C, C.F64, 0, n, batch, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     plan.exec_device(C.FORWARD, (x.data_ptr(), None), (spec.data_ptr(), None))
     plan.exec_device(C.INVERSE, (spec.data_ptr(), None), (back.data_ptr(), None))      # f64 c2r: extension, round trip only
     plan.sync()

@@ -234,6 +234,7 @@ def test_unused_second_plane_pointer_is_ignored(wf, oracle):
     x = torch.rand(b * n, device="cuda")
     spec = torch.empty(b * (n + 2), device="cuda")
     p = wf.Plan(C.R2C, C.F32, 0, n, b, 0, C.PLAN_NO_HOST_BUFFERS | C.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     p.exec_device(C.FORWARD, (x.data_ptr(), 0x3), (spec.data_ptr(), 0x7))
     torch.cuda.synchronize()
     g = spec.cpu().numpy().reshape(b, n + 2)
@@ -250,6 +251,7 @@ def test_stft_unaligned_sample_pointer(wf, oracle):
     n_fft, hop, ns = 256, 64, 4096
     buf = torch.rand(ns + 1, device="cuda") * 2 - 1
     sp = wf.Spectrogram(ns, n_fft, hop, "hann", mode="complex", flags=wf._cabi.PLAN_NO_HOST_BUFFERS | wf._cabi.PLAN_NO_DEVICE_BUFFERS)
+    torch.cuda.synchronize()      # torch filled the inputs on ITS stream; the plan's stream is non-blocking
     out = torch.empty(sp.numFrames * sp.numBins * 2, device="cuda")
     sp.run_device(buf.data_ptr() + 4, out.data_ptr())
     torch.cuda.synchronize()

@@ -1559,6 +1559,9 @@ template <typename R, class PL, int PADQ, int X, bool C2R> __host__ __device__ c
 // bulk store after the next loop-top barrier.  r2c: each row's (M+1) bins; the mirrored halves are parked in the
 // row's own slots [1, M/2], and the thread that reads park[k] is the one that overwrites it with X[k], so the
 // post-process is in place.  c2r: the M complex (= N real) outputs of each row.
+#ifndef WFB_REAL_DENSE
+#define WFB_REAL_DENSE 0           // 1: the dense side of every tile as one block (A/B builds; see GROUPED below)
+#endif
 template <typename R, class PL, int X, int PADQ, bool C2R, int MINB, bool RC = false, bool TS = false, bool HT = false>
 __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_constant__ KParams p) {
     static_assert(PL::valid() && RT<R>::LANES == 1, "scalar lanes only");
@@ -1585,8 +1588,21 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
     // ((M+1) bins), so rows h, h+T, ... land in disjoint bank ranges, while adjacent rows would overlap in all but one
     // bank (ncu: 2-way conflicts on every park/result access at N = 256).  Row of the tile this group works on:
     constexpr int PHL = 128 / (int)sizeof(typename VecOf<R>::v2);     // lanes per phase
-    constexpr bool ROWMAP = !C2R && TS && PL::T < PHL && X % PHL == 0;
+    // GROUPED: the DENSE side of such a tile (the r2c input rows, the c2r result rows: stride M bins, a multiple of 32
+    // banks) would put the two thread groups of a phase on the same banks whatever rows they take (ncu r02, N = 256:
+    // 33 / 40 % of the shared-memory wavefronts replayed, pipe at 90 / 94 %).  With exactly two groups per phase the dense
+    // side therefore moves in groups of T rows, one bulk copy each, with 64 bytes of padding behind every group: rows a
+    // and a + T then sit 16 banks apart.  The c2r direction uses the same row mapping (its (M+1)-bin input rows are the
+    // odd-stride side there).
+    constexpr bool GROUPED = TS && !RC && X > 1 && PL::T < PHL && PHL / PL::T == 2 && X % PHL == 0 && !WFB_REAL_DENSE;
+    constexpr bool ROWMAP = (!C2R || GROUPED) && TS && PL::T < PHL && X % PHL == 0;
     const int xr = ROWMAP ? ((xi / (PHL / PL::T)) / PL::T) * PHL + (xi / (PHL / PL::T)) % PL::T + PL::T * (xi % (PHL / PL::T)) : xi;
+    constexpr int GPAD = 64 / (int)sizeof(typename VecOf<R>::v2);                  // padding behind a dense-side group, bins
+    constexpr int GSTR = PL::T * M + GPAD;                                           // dense-side group stride, bins
+    constexpr int NGRP = X / PL::T;                                                  // dense-side groups per tile
+    static_assert(!GROUPED || (size_t)NGRP * GSTR * sizeof(typename VecOf<R>::v2) <= real_pipe_buf_bytes<R, PL, PADQ, X, C2R>(),
+                  "the padded dense side must fit the stage buffer (sized for the scratch)");
+    const int doff = GROUPED ? (xr / PL::T) * GSTR + (xr % PL::T) * M : xr * M;      // my dense-side row, bins
     const typename RT<R>::twel *tw = reinterpret_cast<const typename RT<R>::twel *>(p.tw);
     const typename RT<R>::twel *rtw = reinterpret_cast<const typename RT<R>::twel *>(p.rtw);
     const long tiles = (p.batch + X - 1) / X;
@@ -1612,6 +1628,15 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
                 const uint32_t bytes = (uint32_t)((M + 2) * sizeof(V2));
                 mbar_expect_tx(mbar + st, bytes);
                 tma_load_1d(smem_raw + st * BUF, gin + tile * IN_ROW - (tile & 1), bytes, mbar + st);
+            }
+        } else if constexpr (GROUPED && !C2R) {
+            if (threadIdx.x == 0) {                   // the dense time-domain side: one copy per group of T rows
+                mbar_expect_tx(mbar + st, (uint32_t)(rows * M * sizeof(V2)));
+                for (int g = 0; g * PL::T < rows; g++) {
+                    const int nr = rows - g * PL::T < PL::T ? rows - g * PL::T : PL::T;
+                    tma_load_1d(smem_raw + st * BUF + (size_t)g * GSTR * sizeof(V2), gin + (tile * X + (long)g * PL::T) * M,
+                                (uint32_t)(nr * M * sizeof(V2)), mbar + st);
+                }
             }
         } else if constexpr (!RC) {
             if (threadIdx.x == 0) {
@@ -1640,7 +1665,16 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
         const int count = tile_rows(tile) * OUT_ROW;
         const V2 *src = reinterpret_cast<const V2 *>(smem_raw + st * BUF);
         V2 *dst = gout + tile * X * OUT_ROW;
-        if constexpr (ROW1) {
+        if constexpr (GROUPED && C2R) {
+            if (threadIdx.x == 0) {                   // the dense time-domain side: one store per group of T rows
+                const int rows = tile_rows(tile);
+                for (int g = 0; g * PL::T < rows; g++) {
+                    const int nr = rows - g * PL::T < PL::T ? rows - g * PL::T : PL::T;
+                    tma_store_1d(dst + (size_t)g * PL::T * M, src + (size_t)g * GSTR, (uint32_t)(nr * M * sizeof(V2)));
+                }
+                bulk_commit();
+            }
+        } else if constexpr (ROW1) {
             if (threadIdx.x == 0) {
                 const int sh = (int)(tile & 1);
                 tma_store_1d(dst + sh, src + 2 * sh, (uint32_t)(M * sizeof(V2)));
@@ -1684,7 +1718,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
         const long row = tile * X + xr;
         const bool active = row < p.batch;
         cx<R> *scratch = reinterpret_cast<cx<R> *>(buf) + (size_t)xi * padded_size<PADQ>(M);
-        const V2 *raw = reinterpret_cast<const V2 *>(buf) + (size_t)xr * RSTR + ((SHIFT && tma_ok(tile)) ? (int)(tile & 1) : 0);
+        const V2 *raw = reinterpret_cast<const V2 *>(buf) + ((GROUPED && !C2R) ? (size_t)doff : (size_t)xr * RSTR) + ((SHIFT && tma_ok(tile)) ? (int)(tile & 1) : 0);
 
         if constexpr (!C2R) {
             // ---------------- r2c
@@ -1770,7 +1804,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_real_pipe(const __grid_const
             run_all<R, PL, PADQ, X, true>(x, tw, UTw<R, PL>::make(p, tw), scratch, tid, xi, true, hsrc);
             if constexpr (TS) {
                 if constexpr (X > 1) __syncthreads(); else sync_transform<PL::T, X>(xi);   // result rows alias the scratch
-                V2 *z = reinterpret_cast<V2 *>(buf) + (size_t)xi * M + tid;
+                V2 *z = reinterpret_cast<V2 *>(buf) + (GROUPED ? (size_t)doff : (size_t)xi * M) + tid;
                 static_for<PL::E>([&](auto S_) {
                     CIDX(slot_, S_);
                     constexpr int e = out_elem<PL, LAST>(slot_);
