@@ -77,7 +77,7 @@ def test_c2c_f32_many_tiles(wf, oracle, n, layout):
 
 
 @pytest.mark.parametrize("layout", ["split", "interleaved"])
-@pytest.mark.parametrize("n,tag", [(2048, "_rpf"), (4096, "_rpf"), (128, "_ts_g")])
+@pytest.mark.parametrize("n,tag", [(2048, "_rpf"), (4096, "_rpf"), (128, "_ts_g"), (256, "_ts_g"), (512, "_ts_g")])
 def test_c2c_f32_alternate_persistent_kernels_many_tiles(wf, oracle, n, tag, layout):
     """Persistent alternates of the default kernel on the same plan: the register-prefetch kernels (k_c2c_rpf: the next
     transform is loaded into a second register set while the current one is computed; results leave through two alternating

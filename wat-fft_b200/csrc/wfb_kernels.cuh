@@ -1036,7 +1036,7 @@ __global__ void __launch_bounds__(PL::T *X, MINB) k_c2c_pipe(const __grid_consta
     // of the instructions in those loops).
     constexpr int RG = RC > 0 ? RC : 1;             // rows per copy group
     constexpr int NGR = ROWS / RG;                  // groups per tile
-    constexpr int GSTR = RG * N + N / 16;           // smem group stride, elements (RC only)
+    constexpr int GSTR = RG * N + (PL::T < 32 ? PL::T : N / 16);   // smem group stride, elements (RC only): groups T banks apart
     constexpr int PSTR = RC ? NGR * GSTR : ROWS * N;   // plane stride (split layout), elements
     static_assert(!RC || (ROWS % RG == 0 && NGR >= 32 / PL::T && LANES == 1), "a warp's thread groups must land in distinct copy groups");
     static_assert(!RC || (size_t)(IO == IO_SPLIT ? 2 : 1) * NGR * GSTR * (IO == IO_SPLIT ? 1 : 2) * sizeof(typename VecOf<R>::s) <= pipe_buf_bytes<R, PL, PADQ, X>(),

@@ -7,7 +7,7 @@ namespace wfb {
 #define VP32(PL, X, MINB, PRIO) PipeLaunchers<float, PL, X, MINB, 0, 32>::make(#PL "_pipe" #X, PRIO)
 #define VTS(PL, X, MINB, RC, PQ, PRIO) PipeLaunchers<float, PL, X, MINB, RC, PQ, true>::make(#PL "_pipe" #X "_ts", PRIO)
 // row copies in groups of RG rows per bulk copy (see RC in k_c2c_pipe)
-#define VTSG(PL, X, MINB, RG, PQ, PRIO) PipeLaunchers<float, PL, X, MINB, RG, PQ, true>::make(#PL "_pipe" #X "_ts_g" #RG, PRIO)
+#define VTSG(PL, X, MINB, RG, PQ, ...) PipeLaunchers<float, PL, X, MINB, RG, PQ, true>::make(#PL "_pipe" #X "_ts_g" #RG, __VA_ARGS__)
 #define VTSM(PL, X, MINB, RC, PQ, PRIO) PipeLaunchers<float, PL, X, MINB, RC, PQ, true>::make(#PL "_pipe" #X "_ts_m" #MINB, PRIO)
 #define VRP(PL, MINB, TS, NAME, PRIO) RegPipeLaunchers<float, PL, MINB, TS>::make(#PL NAME, PRIO)
 #define VP2(PL, X, MINB, PRIO) PipeLaunchers<f32x2, PL, X, MINB>::make(#PL "_pipe" #X "_x2", PRIO)
@@ -29,7 +29,13 @@ const std::vector<Variant> &variants_f32_pipe() {
         // N = 128: row copies in groups of 2 rows (32 bulk copies per tile and direction instead of 64): 177 -> 156 M executed
         // instructions per launch, power-capped split 0.92 / 0.91 -> 1.00 / 1.00 (fwd / inv), burst and interleaved unchanged
         // (1.03); groups of 4 (145 M instructions): 1.00 / 0.99
-        VTSG(F32_128, 16, 2, 2, 16, 61), VTS(F32_128, 16, 2, 1, 16, 60), VTSG(F32_128, 16, 2, 4, 16, 59), VTS(F32_256, 8, 2, 0, 16, 60), VTS(P32_512, 4, 2, 0, 16, 60), VTS(P32_1024, 2, 2, 0, 32, 60),
+        VTSG(F32_128, 16, 2, 2, 16, 61), VTS(F32_128, 16, 2, 1, 16, 60), VTSG(F32_128, 16, 2, 4, 16, 59),
+        // N = 256, 512 (T = 16): on the split planes a warp reads two rows side by side with 32-bit accesses, and in a
+        // dense tile both sit on the same banks (ncu: 41 % of the shared-memory wavefronts replayed at both sizes).
+        // Grouped copies put them 16 banks apart: power-capped 512 0.996 -> 1.016, 256 1.002 -> 1.004 on a fast box
+        // (HBM-bound there); burst 1.040 -> 1.040 / 1.030 -> 1.023.  Defaults for the split layout; the interleaved
+        // layout (64-bit accesses: one row per half-warp, no conflict) keeps the dense tile.
+        VTSG(F32_256, 8, 2, 4, 16, 61, -1, 58), VTSG(P32_512, 4, 2, 2, 16, 61, -1, 58), VTS(F32_256, 8, 2, 0, 16, 60), VTS(P32_512, 4, 2, 0, 16, 60), VTS(P32_1024, 2, 2, 0, 32, 60),
         VTS(F32_2048, 1, 4, 0, 16, 60), VTS(P64_4096, 1, 1, 0, 64, 20), VTS(F32_4096, 1, 2, 0, 16, 60), VTS(F32_8192, 1, 1, 0, 16, 60),
         // N = 8192: three passes (32 values per thread) instead of four: 69 -> 82 %
         VTS(P32_8192, 1, 1, 0, 16, 61),
