@@ -132,6 +132,100 @@ def registered_plans():
     return out
 
 
+# ----------------------------------------------------------------------------------------
+# Tile I/O: the accesses with which the threads read a staged tile into registers (and write the result tile back).
+# The exchange patterns above are private to one transform; these depend on how the ROWS of a tile lie in the stage
+# buffer relative to each other, because with T < 32 threads per transform a warp touches several rows at once.
+# ----------------------------------------------------------------------------------------
+def c2c_tile_rows(N, T, X, RG):
+    """k_c2c_pipe: thread group xi -> (row of the tile, element offset of that row in its plane).
+    RG = 0: dense tile; RG > 0: groups of RG rows, (T if T < 32 else N/16) elements of padding behind each group, the
+    32/T thread groups of a warp in different groups."""
+    out = []
+    for xi in range(X):
+        if RG:
+            ngr = X // RG
+            xr = (xi % ngr) * RG + xi // ngr
+            gstr = RG * N + (T if T < 32 else N // 16)
+            out.append((xr, (xr // RG) * gstr + (xr % RG) * N))
+        else:
+            out.append((xi, xi * N))
+    return out
+
+
+def c2c_tile_io(N, T, X, RG, layout):
+    """worst wavefront multiplicity of the input reads / result writes of a k_c2c_pipe tile.
+    layout 'split': one 32-bit access per plane and element; 'il': one 64-bit access per element."""
+    E = N // T
+    rows = c2c_tile_rows(N, T, X, RG)
+    assert sorted(r for r, _ in rows) == list(range(X))
+    words = 1 if layout == "split" else 2
+    worst = 1.0
+    for e in range(E):
+        for w0 in range(0, T * X, 32):
+            addrs = []
+            for lane in range(32):
+                th = w0 + lane
+                if th >= T * X:
+                    addrs.append(None)
+                    continue
+                xi, tid = th // T, th % T
+                addrs.append((rows[xi][1] + tid + e * T) * words)
+            c, ideal = conflicts(addrs, words)
+            worst = max(worst, c / ideal)
+    return worst
+
+
+def real_tile_rows(M, T, X, elem_bytes, grouped):
+    """k_real_pipe with bulk stores: thread group xi -> (row, offset of the row on the DENSE side in bins).  With fewer
+    than a phase of lanes per transform the groups sharing a phase take rows T apart (ROWMAP); `grouped`: the dense side in
+    groups of T rows with 64 bytes of padding behind each."""
+    phl = 128 // (2 * elem_bytes)
+    out = []
+    for xi in range(X):
+        xr = xi
+        if T < phl and X % phl == 0:
+            gp = phl // T
+            q = xi // gp
+            xr = (q // T) * phl + q % T + T * (xi % gp)
+        if grouped:
+            gstr = T * M + 64 // (2 * elem_bytes)
+            out.append((xr, (xr // T) * gstr + (xr % T) * M))
+        else:
+            out.append((xr, xr * M))
+    return out
+
+
+def real_tile_io(M, T, X, elem_bytes, grouped):
+    """worst multiplicity on the dense side (r2c input reads / c2r result writes) and on the (M+1)-bin side"""
+    E = M // T
+    rows = real_tile_rows(M, T, X, elem_bytes, grouped)
+    words = 2 * elem_bytes // 4
+    worst_dense = worst_odd = 1.0
+    for e in range(E):
+        for w0 in range(0, T * X, 32):
+            dense, odd = [], []
+            for lane in range(32):
+                th = w0 + lane
+                if th >= T * X:
+                    dense.append(None); odd.append(None)
+                    continue
+                xi, tid = th // T, th % T
+                dense.append((rows[xi][1] + tid + e * T) * words)
+                odd.append((rows[xi][0] * (M + 1) + tid + e * T) * words)
+            c, ideal = conflicts(dense, words)
+            worst_dense = max(worst_dense, c / ideal)
+            c, ideal = conflicts(odd, words)
+            worst_odd = max(worst_odd, c / ideal)
+    return worst_dense, worst_odd
+
+
+# default kernels of csrc/wfb_variants_f32_pipe.cu: (N, T, rows per tile, rows per copy group for split / interleaved)
+C2C_F32_TILES = {128: (8, 16, 2, 2), 256: (16, 8, 4, 0), 512: (16, 4, 2, 0), 1024: (32, 2, 0, 0), 2048: (128, 1, 0, 0), 4096: (256, 1, 0, 0)}
+# k_real_pipe defaults whose thread groups share a phase: (M, T, X, bytes per real)
+REAL_TILES_GROUPED = {"r2c/c2r f32 N=256": (128, 8, 16, 4), "r2c/c2r f64 N=128": (64, 4, 16, 8)}
+
+
 if __name__ == "__main__":
     for name, plans, ew in (("f32", PLANS_F32, 2), ("f64", PLANS_F64, 4)):
         for padq in (0, 4, 8, 16, 32):
