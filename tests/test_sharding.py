@@ -42,6 +42,21 @@ def test_rank_device_orders(wf):
         rank_device(2, 2, 8)
 
 
+def test_grains_tile_the_batch(wf):
+    from watfft_b200.sharding import grains
+    for batch in (0, 1, 255, 256, 1000, 10007, 262144):
+        for row_bytes in (64, 1024, 16384):
+            for grain_bytes in (64 << 10, 1 << 20, 32 << 20):
+                g, lst = grains(batch, row_bytes, grain_bytes)
+                assert g >= 1 and (g < 512 or g % 256 == 0)
+                assert sum(r for _, r in lst) == batch
+                assert all(r0 == i * g for i, (r0, _) in enumerate(lst))
+                assert all(r == g for _, r in lst[:-1]) and (not lst or 1 <= lst[-1][1] <= g)
+    assert grains(262144, 16384, 32 << 20) == (2048, [(i * 2048, 2048) for i in range(128)])     # configs[4]: 128 grains
+    with pytest.raises(ValueError):
+        grains(10, 0)
+
+
 def test_world_size_2_gloo(tmp_path):
     script = tmp_path / "rank.py"
     script.write_text(textwrap.dedent(f"""

@@ -44,6 +44,18 @@ def rank_device(local_rank: int, world: int, visible: int, order: str = "spread"
     return local_rank
 
 
+def grains(batch: int, row_bytes: int, grain_bytes: int = 32 << 20):
+    """Row ranges [(first row, rows)] of the pulled-grain schedule (ShardedSplitFFT schedule="dynamic"): grains of
+    `grain_bytes` per plane, whole kernel tiles (multiples of 256 rows) once a grain holds 512 rows or more, the last
+    grain whatever is left.  Returns (rows per full grain, list)."""
+    if batch < 0 or row_bytes < 1 or grain_bytes < 1:
+        raise ValueError("bad grain request")
+    g = max(1, grain_bytes // row_bytes)
+    if g >= 512:
+        g &= ~255
+    return g, [(r0, min(g, batch - r0)) for r0 in range(0, batch, g)]
+
+
 def max_over_ranks(value: float, backend_group=None) -> float:
     """Timing reduction used by bench.py: the job time is the slowest rank's time."""
     import torch
@@ -83,11 +95,8 @@ class ShardedSplitFFT:
         self._mem = [HostMemory(max(1, batch) * row), HostMemory(max(1, batch) * row)]
         self.real = self._mem[0].view(np.float32, 0, batch * size).reshape(batch, size)
         self.imag = self._mem[1].view(np.float32, 0, batch * size).reshape(batch, size)
-        g = max(1, grain_bytes // row)
-        if g >= 512:
-            g &= ~255                                  # whole kernel tiles per grain
-        self.grain = g
-        self.grains = [(r0, min(g, batch - r0)) for r0 in range(0, batch, g)]
+        self.grain, self.grains = grains(batch, row, grain_bytes)
+        g = self.grain
         flags = C.PLAN_NO_HOST_BUFFERS
         self.workers = []                              # (device slot, plan for full grains)
         for slot, d in enumerate(self.devices):
